@@ -1,0 +1,453 @@
+// C-ABI of the CAVIAR pair-feature path (see include/caviar_b200.h).  Build:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC cv_api.cu -o libcaviar_b200.so
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/caviar_b200.h"
+#include "cv_device.cuh"
+#include "cv_plan.hpp"
+
+using namespace cv;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static thread_local int64_t g_launches = 0;
+
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CV_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(CV_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));            \
+    } while (0)
+
+extern "C" const char* caviar_last_error(void) { return g_err.c_str(); }
+extern "C" int caviar_abi_version(void) { return CV_ABI_VERSION; }
+extern "C" int64_t caviar_last_launch_count(void) { return g_launches; }
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+struct CvPlan {
+    HostPlan hp;
+    int device = 0;
+    TileDesc* d_tiles = nullptr;
+    CtaDesc* d_ctas = nullptr;
+    int32_t *d_idx0 = nullptr, *d_idx1 = nullptr, *d_idx2 = nullptr;
+    int32_t* d_src_off = nullptr;
+    int* d_err = nullptr;
+    std::once_flag smem_once;
+};
+
+extern "C" int caviar_plan_describe(const CvPlanDesc* desc, int32_t n_sms, CvPlanInfo* info) {
+    if (!desc || !info) return fail(CV_E_INVALID, "null argument");
+    HostPlan hp;
+    std::string why = build_plan(*desc, n_sms, hp);
+    if (!why.empty()) return fail(CV_E_INVALID, why);
+    fill_info(hp, *info);
+    return CV_OK;
+}
+
+template <typename T>
+static cudaError_t upload(T** dst, const std::vector<T>& src) {
+    *dst = nullptr;
+    if (src.empty()) return cudaSuccess;
+    cudaError_t e = cudaMalloc((void**)dst, src.size() * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+extern "C" void caviar_plan_destroy(CvPlan* plan) {
+    if (!plan) return;
+    cudaFree(plan->d_tiles); cudaFree(plan->d_ctas);
+    cudaFree(plan->d_idx0); cudaFree(plan->d_idx1); cudaFree(plan->d_idx2);
+    cudaFree(plan->d_src_off); cudaFree(plan->d_err);
+    delete plan;
+}
+
+extern "C" int caviar_plan_create(const CvPlanDesc* desc, CvPlan** out) {
+    if (!desc || !out) return fail(CV_E_INVALID, "null argument");
+    *out = nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+        return fail(CV_E_NO_DEVICE, "no CUDA device: caviar_b200 has no CPU fallback");
+    int dev = desc->device;
+    if (dev < 0) CV_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CV_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        return fail(CV_E_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100: this library ships sm_100a code only");
+    CV_CUDA(cudaSetDevice(dev));
+    CvPlan* p = new (std::nothrow) CvPlan();
+    if (!p) return fail(CV_E_NOMEM, "out of host memory");
+    p->device = dev;
+    std::string why = build_plan(*desc, prop.multiProcessorCount, p->hp);
+    if (!why.empty()) { delete p; return fail(CV_E_INVALID, why); }
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = upload(&p->d_tiles, p->hp.tiles);
+    if (e == cudaSuccess) e = upload(&p->d_ctas, p->hp.ctas);
+    if (e == cudaSuccess) e = upload(&p->d_idx0, p->hp.idx0);
+    if (e == cudaSuccess) e = upload(&p->d_idx1, p->hp.idx1);
+    if (e == cudaSuccess) e = upload(&p->d_idx2, p->hp.idx2);
+    if (e == cudaSuccess) e = upload(&p->d_src_off, p->hp.src_off);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_err, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(p->d_err, 0, sizeof(int));
+    if (e != cudaSuccess) {
+        std::string msg = std::string("plan upload: ") + cudaGetErrorString(e);
+        caviar_plan_destroy(p);
+        return fail(CV_E_CUDA, msg);
+    }
+    *out = p;
+    return CV_OK;
+}
+
+extern "C" int caviar_plan_info(const CvPlan* plan, CvPlanInfo* info) {
+    if (!plan || !info) return fail(CV_E_INVALID, "null argument");
+    fill_info(plan->hp, *info);
+    return CV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// box records / staging
+// ------------------------------------------------------------------------------------------------
+extern "C" int caviar_prepare_box(const CvPlan* plan, const float* box_dev, int64_t n_frames, float* boxrec_dev,
+                                  void* stream) {
+    if (!plan) return fail(CV_E_INVALID, "null plan");
+    g_launches = 0;
+    if (plan->hp.desc.box_kind == CV_BOX_NONE) return CV_OK;
+    if (n_frames <= 0) return CV_OK;
+    if (!box_dev || !boxrec_dev) return fail(CV_E_INVALID, "null box pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    CV_CUDA(cudaMemsetAsync(plan->d_err, 0, sizeof(int), st));
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((n_frames + threads - 1) / threads);
+    box_prepare_kernel<<<blocks, threads, 0, st>>>(box_dev, n_frames, plan->hp.desc.box_kind, boxrec_dev, plan->d_err);
+    CV_CUDA(cudaGetLastError());
+    g_launches = 1;
+    int err = 0;
+    CV_CUDA(cudaMemcpyAsync(&err, plan->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CV_CUDA(cudaStreamSynchronize(st));
+    if (err & 1) return fail(CV_E_UNSUPPORTED, "triclinic cell is not lower triangular (a along x, b in the xy plane)");
+    if (err & 2) return fail(CV_E_INVALID, "box with a non-positive edge");
+    if (err & 4) return fail(CV_E_UNSUPPORTED, "cell too skewed: more than 16 lattice translations would have to be searched");
+    return CV_OK;
+}
+
+extern "C" int caviar_stage_frames(const CvPlan* plan, const float* xyz_dev, int64_t frame_stride_floats,
+                                   int64_t n_frames, float* staged_dev, void* stream) {
+    if (!plan) return fail(CV_E_INVALID, "null plan");
+    g_launches = 0;
+    if (plan->hp.mode != CV_MODE_STAGED) return fail(CV_E_INVALID, "plan does not use the staged layout");
+    if (n_frames <= 0) return CV_OK;
+    if (!xyz_dev || !staged_dev) return fail(CV_E_INVALID, "null coordinate pointer");
+    if (frame_stride_floats < 3ll * plan->hp.desc.n_atoms) return fail(CV_E_INVALID, "frame stride smaller than 3*n_atoms");
+    if ((reinterpret_cast<uintptr_t>(staged_dev) & 15) != 0) return fail(CV_E_INVALID, "staged buffer must be 16-byte aligned");
+    const int S4 = (int)(plan->hp.staged_floats / 4);
+    const int64_t chunk = 65535ll * kStageFramesPerThread;     // grid.y is limited to 65535 blocks
+    for (int64_t t0 = 0; t0 < n_frames; t0 += chunk) {
+        const int64_t n = std::min<int64_t>(chunk, n_frames - t0);
+        dim3 grid((S4 + 255) / 256, (unsigned)((n + kStageFramesPerThread - 1) / kStageFramesPerThread));
+        stage_frames_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+            xyz_dev + t0 * frame_stride_floats, frame_stride_floats, n,
+            reinterpret_cast<const int4*>(plan->d_src_off), S4,
+            reinterpret_cast<float4*>(staged_dev + t0 * plan->hp.staged_floats));
+        CV_CUDA(cudaGetLastError());
+        g_launches += 1;
+    }
+    return CV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the fused run
+// ------------------------------------------------------------------------------------------------
+template <int BOX, bool PIPE>
+static cudaError_t launch_features(const CvPlan* plan, const RunParams& rp, cudaStream_t st) {
+    auto kern = features_kernel<BOX, PIPE>;
+    const int threads = PIPE ? kConsumerThreads + kProducerThreads : kConsumerThreads;
+    const int smem = PIPE ? plan->hp.smem_bytes : 0;
+    if (PIPE) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<plan->hp.n_ctas, threads, smem, st>>>(rp);
+    return cudaGetLastError();
+}
+
+extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t frame_stride_floats,
+                          const float* boxrec_dev, int64_t n_frames, const CvFrameOutputs* out,
+                          const CvAggregates* agg, void* workspace_dev, void* stream) {
+    g_launches = 0;
+    if (!plan) return fail(CV_E_INVALID, "null plan");
+    if (n_frames < 0) return fail(CV_E_INVALID, "negative frame count");
+    if (n_frames == 0) return CV_OK;
+    const HostPlan& hp = plan->hp;
+    if (!coords_dev) return fail(CV_E_INVALID, "null coordinate pointer");
+    if (hp.desc.box_kind != CV_BOX_NONE && !boxrec_dev) return fail(CV_E_INVALID, "plan has a box but boxrec is null");
+    const bool want_agg = agg && (agg->occupancy || agg->sum || agg->sumsq);
+    if (want_agg && !(agg->occupancy && agg->sum && agg->sumsq)) return fail(CV_E_INVALID, "aggregates are all-or-none");
+    if (want_agg && !workspace_dev) return fail(CV_E_INVALID, "aggregates need a workspace");
+    cudaStream_t st = (cudaStream_t)stream;
+
+    RunParams rp{};
+    rp.coords = coords_dev;
+    rp.boxrec = boxrec_dev;
+    rp.n_frames = n_frames;
+    if (hp.mode == CV_MODE_STAGED) {
+        rp.frame_stride = hp.staged_floats;
+    } else {
+        if (frame_stride_floats < 3ll * hp.desc.n_atoms) return fail(CV_E_INVALID, "frame stride smaller than 3*n_atoms");
+        if (hp.mode == CV_MODE_ZEROCOPY && frame_stride_floats != 3ll * hp.desc.n_atoms)
+            return fail(CV_E_INVALID, "zero-copy mode needs densely packed frames (stride == 3*n_atoms)");
+        rp.frame_stride = frame_stride_floats;
+    }
+    if (hp.mode != CV_MODE_DIRECT) {
+        if ((reinterpret_cast<uintptr_t>(coords_dev) & 15) != 0) return fail(CV_E_INVALID, "coordinates must be 16-byte aligned for TMA");
+        if (boxrec_dev && (reinterpret_cast<uintptr_t>(boxrec_dev) & 15) != 0) return fail(CV_E_INVALID, "box records must be 16-byte aligned");
+    }
+    rp.tiles = plan->d_tiles; rp.ctas = plan->d_ctas;
+    rp.idx0 = plan->d_idx0; rp.idx1 = plan->d_idx1; rp.idx2 = plan->d_idx2;
+    rp.n_tiles = (int)hp.tiles.size();
+    rp.frames_per_stage = hp.frames_per_stage; rp.n_stages = hp.n_stages; rp.stage_floats = hp.stage_floats;
+    rp.whole_frame = hp.whole_frame;
+    if (out) { rp.dist = out->dist; rp.angle = out->angle; rp.flags = out->flags; rp.score = out->score; }
+    rp.P = hp.P; rp.A = hp.A; rp.W = hp.W; rp.Wp = hp.Wp;
+    const long long F = hp.P + hp.A;
+    if (want_agg) {
+        rp.occ_part = reinterpret_cast<unsigned long long*>(workspace_dev);
+        rp.sum_part = reinterpret_cast<double*>(rp.occ_part + (long long)hp.partial_slots * F);
+        rp.sq_part = rp.sum_part + (long long)hp.partial_slots * F;
+    }
+    rp.pair_thr = hp.pair_thr; rp.hb_dthr = hp.hb_dthr; rp.hb_athr = hp.hb_athr;
+
+    if (rp.score) CV_CUDA(cudaMemsetAsync(rp.score, 0, sizeof(int32_t) * n_frames, st));
+
+    cudaError_t e;
+    const bool pipe = hp.mode != CV_MODE_DIRECT;
+    switch (hp.desc.box_kind * 2 + (pipe ? 1 : 0)) {
+        case 0: e = launch_features<0, false>(plan, rp, st); break;
+        case 1: e = launch_features<0, true>(plan, rp, st); break;
+        case 2: e = launch_features<1, false>(plan, rp, st); break;
+        case 3: e = launch_features<1, true>(plan, rp, st); break;
+        case 4: e = launch_features<2, false>(plan, rp, st); break;
+        default: e = launch_features<2, true>(plan, rp, st); break;
+    }
+    if (e != cudaSuccess) return fail(CV_E_CUDA, std::string("features_kernel launch: ") + cudaGetErrorString(e));
+    g_launches += 1;
+    if (want_agg) {
+        const unsigned blocks = (unsigned)((F + 255) / 256);
+        finalize_kernel<<<blocks, 256, 0, st>>>(rp.occ_part, rp.sum_part, rp.sq_part, hp.P, hp.A, hp.pair_tile_w,
+                                                hp.trip_tile_w, hp.n_pair_tiles, plan->d_tiles,
+                                                reinterpret_cast<unsigned long long*>(agg->occupancy), agg->sum, agg->sumsq);
+        CV_CUDA(cudaGetLastError());
+        g_launches += 1;
+    }
+    return CV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reference-facing host entry points
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    cudaError_t alloc(size_t bytes) { return bytes ? cudaMalloc(&p, bytes) : cudaSuccess; }
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+struct PinBuf {
+    void* p = nullptr;
+    cudaError_t alloc(size_t bytes) { return bytes ? cudaMallocHost(&p, bytes) : cudaSuccess; }
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+struct Stream {
+    cudaStream_t s = nullptr;
+    cudaError_t create() { return cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking); }
+    ~Stream() { if (s) cudaStreamDestroy(s); }
+};
+struct Event {
+    cudaEvent_t e = nullptr;
+    cudaError_t create() { return cudaEventCreateWithFlags(&e, cudaEventDisableTiming); }
+    ~Event() { if (e) cudaEventDestroy(e); }
+};
+bool is_pinned(const void* p) {
+    if (!p) return true;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+}  // namespace
+
+// Block loop with two device buffer sets: while block b computes, block b+1 is uploaded and block b-1 is
+// downloaded.  Pageable host memory goes through pinned bounce buffers (one memcpy each way); memory the
+// caller pinned (cudaHostAlloc / cudaHostRegister / torch pin_memory) is DMA'd in place.
+extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, int64_t frame_stride_floats,
+                                    const float* box_host, int64_t n_frames, const CvHostOutputs* out,
+                                    int64_t frames_per_block) {
+    g_launches = 0;
+    if (!plan || !out) return fail(CV_E_INVALID, "null argument");
+    if (n_frames < 0) return fail(CV_E_INVALID, "negative frame count");
+    const HostPlan& hp = plan->hp;
+    const int64_t P = hp.P, A = hp.A, W = hp.W, F = P + A;
+    const int box_kind = hp.desc.box_kind;
+    const int box_floats = box_kind == CV_BOX_ORTHO ? 3 : (box_kind == CV_BOX_TRICLINIC ? 9 : 0);
+    if (n_frames > 0 && !xyz_host) return fail(CV_E_INVALID, "null coordinates");
+    if (box_kind != CV_BOX_NONE && n_frames > 0 && !box_host) return fail(CV_E_INVALID, "plan has a box but box_host is null");
+    if (frame_stride_floats < 3ll * hp.desc.n_atoms) return fail(CV_E_INVALID, "frame stride smaller than 3*n_atoms");
+    const bool want_agg = out->occupancy || out->sum || out->sumsq;
+    if (want_agg && !(out->occupancy && out->sum && out->sumsq)) return fail(CV_E_INVALID, "aggregates are all-or-none");
+    CV_CUDA(cudaSetDevice(plan->device));
+
+    // block size: ~256 MB of input + output per buffer set
+    const int64_t in_row = frame_stride_floats * 4 + box_floats * 4;
+    const int64_t out_row = (out->dist ? 4 * P : 0) + (out->angle ? 4 * A : 0) + (out->flags ? 4 * W : 0) + (out->score ? 4 : 0);
+    int64_t TB = frames_per_block > 0 ? frames_per_block : std::max<int64_t>(64, (256ll << 20) / std::max<int64_t>(1, in_row + out_row));
+    TB = std::max<int64_t>(1, std::min<int64_t>(TB, std::max<int64_t>(n_frames, 1)));
+    const bool in_pinned = is_pinned(xyz_host);
+    const bool out_pinned = is_pinned(out->dist) && is_pinned(out->angle) && is_pinned(out->flags) && is_pinned(out->score);
+
+    struct Set {
+        DevBuf xyz, staged, dist, angle, flags, score;
+        PinBuf h_in, h_dist, h_angle, h_flags, h_score;
+        Event uploaded, computed, downloaded;
+    } set[2];
+    DevBuf ws, occ, sum, sq, box_all, rec_all;
+    Stream s_up, s_run, s_down;
+    CV_CUDA(s_up.create()); CV_CUDA(s_run.create()); CV_CUDA(s_down.create());
+    for (Set& s : set) {
+        CV_CUDA(s.xyz.alloc((size_t)TB * frame_stride_floats * 4));
+        CV_CUDA(s.staged.alloc(hp.mode == CV_MODE_STAGED ? (size_t)TB * hp.staged_floats * 4 : 0));
+        CV_CUDA(s.dist.alloc(out->dist ? (size_t)TB * P * 4 : 0));
+        CV_CUDA(s.angle.alloc(out->angle ? (size_t)TB * A * 4 : 0));
+        CV_CUDA(s.flags.alloc(out->flags ? (size_t)TB * W * 4 : 0));
+        CV_CUDA(s.score.alloc(out->score ? (size_t)TB * 4 : 0));
+        if (!in_pinned) {
+            CV_CUDA(s.h_in.alloc((size_t)TB * frame_stride_floats * 4));
+        }
+        if (!out_pinned) {
+            CV_CUDA(s.h_dist.alloc(out->dist ? (size_t)TB * P * 4 : 0));
+            CV_CUDA(s.h_angle.alloc(out->angle ? (size_t)TB * A * 4 : 0));
+            CV_CUDA(s.h_flags.alloc(out->flags ? (size_t)TB * W * 4 : 0));
+            CV_CUDA(s.h_score.alloc(out->score ? (size_t)TB * 4 : 0));
+        }
+        CV_CUDA(s.uploaded.create()); CV_CUDA(s.computed.create()); CV_CUDA(s.downloaded.create());
+    }
+    if (want_agg) {
+        CV_CUDA(ws.alloc((size_t)hp.partial_slots * F * 24));
+        CV_CUDA(occ.alloc((size_t)F * 8)); CV_CUDA(sum.alloc((size_t)F * 8)); CV_CUDA(sq.alloc((size_t)F * 8));
+        CV_CUDA(cudaMemsetAsync(occ.p, 0, (size_t)F * 8, s_run.s));
+        CV_CUDA(cudaMemsetAsync(sum.p, 0, (size_t)F * 8, s_run.s));
+        CV_CUDA(cudaMemsetAsync(sq.p, 0, (size_t)F * 8, s_run.s));
+    }
+
+    int64_t launches = 0;
+    if (box_floats && n_frames > 0) {
+        // boxes are tiny (<= 36 B per frame): upload and prepare all records once, outside the block loop
+        CV_CUDA(box_all.alloc((size_t)n_frames * box_floats * 4));
+        CV_CUDA(rec_all.alloc((size_t)n_frames * kRecFloats * 4));
+        CV_CUDA(cudaMemcpyAsync(box_all.p, box_host, (size_t)n_frames * box_floats * 4, cudaMemcpyHostToDevice, s_run.s));
+        int rc = caviar_prepare_box(plan, box_all.as<float>(), n_frames, rec_all.as<float>(), s_run.s);
+        if (rc != CV_OK) return rc;
+        launches += g_launches;
+    }
+    const int64_t n_blocks = (n_frames + TB - 1) / TB;
+    struct Pending { int64_t t0 = 0, n = 0; bool live = false; } pending[2];
+
+    auto drain = [&](int k) -> int {   // copy bounce buffers of set k out to the caller's arrays
+        Pending& pd = pending[k];
+        if (!pd.live) return CV_OK;
+        CV_CUDA(cudaEventSynchronize(set[k].downloaded.e));
+        if (!out_pinned) {
+            if (out->dist) memcpy(out->dist + pd.t0 * P, set[k].h_dist.p, (size_t)pd.n * P * 4);
+            if (out->angle) memcpy(out->angle + pd.t0 * A, set[k].h_angle.p, (size_t)pd.n * A * 4);
+            if (out->flags) memcpy(out->flags + pd.t0 * W, set[k].h_flags.p, (size_t)pd.n * W * 4);
+            if (out->score) memcpy(out->score + pd.t0, set[k].h_score.p, (size_t)pd.n * 4);
+        }
+        pd.live = false;
+        return CV_OK;
+    };
+
+    for (int64_t b = 0; b < n_blocks; ++b) {
+        const int k = (int)(b & 1);
+        Set& s = set[k];
+        const int64_t t0 = b * TB, n = std::min<int64_t>(TB, n_frames - t0);
+        int rc = drain(k);                       // set k is free again once its previous download finished
+        if (rc != CV_OK) return rc;
+        // upload
+        const float* src = xyz_host + t0 * frame_stride_floats;
+        if (!in_pinned) {
+            memcpy(s.h_in.p, src, (size_t)n * frame_stride_floats * 4);
+            src = s.h_in.as<float>();
+        }
+        CV_CUDA(cudaMemcpyAsync(s.xyz.p, src, (size_t)n * frame_stride_floats * 4, cudaMemcpyHostToDevice, s_up.s));
+        CV_CUDA(cudaEventRecord(s.uploaded.e, s_up.s));
+        // compute
+        CV_CUDA(cudaStreamWaitEvent(s_run.s, s.uploaded.e, 0));
+        const float* coords = s.xyz.as<float>();
+        if (hp.mode == CV_MODE_STAGED) {
+            rc = caviar_stage_frames(plan, s.xyz.as<float>(), frame_stride_floats, n, s.staged.as<float>(), s_run.s);
+            if (rc != CV_OK) return rc;
+            launches += g_launches;
+            coords = s.staged.as<float>();
+        }
+        CvFrameOutputs fo{s.dist.as<float>(), s.angle.as<float>(), s.flags.as<uint32_t>(), s.score.as<int32_t>()};
+        CvAggregates ag{occ.as<uint64_t>(), sum.as<double>(), sq.as<double>()};
+        rc = caviar_run(plan, coords, frame_stride_floats, box_floats ? rec_all.as<float>() + t0 * kRecFloats : nullptr, n, &fo, want_agg ? &ag : nullptr, ws.p, s_run.s);
+        if (rc != CV_OK) return rc;
+        launches += g_launches;
+        CV_CUDA(cudaEventRecord(s.computed.e, s_run.s));
+        // download
+        CV_CUDA(cudaStreamWaitEvent(s_down.s, s.computed.e, 0));
+        float* ddst = out_pinned ? out->dist + t0 * P : s.h_dist.as<float>();
+        float* adst = out_pinned ? out->angle + t0 * A : s.h_angle.as<float>();
+        uint32_t* fdst = out_pinned ? out->flags + t0 * W : s.h_flags.as<uint32_t>();
+        int32_t* sdst = out_pinned ? out->score + t0 : s.h_score.as<int32_t>();
+        if (out->dist) CV_CUDA(cudaMemcpyAsync(ddst, s.dist.p, (size_t)n * P * 4, cudaMemcpyDeviceToHost, s_down.s));
+        if (out->angle) CV_CUDA(cudaMemcpyAsync(adst, s.angle.p, (size_t)n * A * 4, cudaMemcpyDeviceToHost, s_down.s));
+        if (out->flags) CV_CUDA(cudaMemcpyAsync(fdst, s.flags.p, (size_t)n * W * 4, cudaMemcpyDeviceToHost, s_down.s));
+        if (out->score) CV_CUDA(cudaMemcpyAsync(sdst, s.score.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s_down.s));
+        CV_CUDA(cudaEventRecord(s.downloaded.e, s_down.s));
+        pending[k] = Pending{t0, n, true};
+        // the next upload into the other set may only start once that set's kernels are done: drain() above
+        // waits for its download, which is ordered after its compute.
+    }
+    for (int k = 0; k < 2; ++k) { int rc = drain(k); if (rc != CV_OK) return rc; }
+    if (want_agg) {
+        CV_CUDA(cudaStreamSynchronize(s_run.s));
+        if (n_frames == 0) { memset(out->occupancy, 0, F * 8); memset(out->sum, 0, F * 8); memset(out->sumsq, 0, F * 8); }
+        CV_CUDA(cudaMemcpy(out->occupancy, occ.p, (size_t)F * 8, cudaMemcpyDeviceToHost));
+        CV_CUDA(cudaMemcpy(out->sum, sum.p, (size_t)F * 8, cudaMemcpyDeviceToHost));
+        CV_CUDA(cudaMemcpy(out->sumsq, sq.p, (size_t)F * 8, cudaMemcpyDeviceToHost));
+    }
+    CV_CUDA(cudaStreamSynchronize(s_run.s));
+    g_launches = launches;
+    return CV_OK;
+}
+
+extern "C" int caviar_pair_distances_host(const float* xyz_host, int64_t n_frames, int32_t n_atoms,
+                                          const int32_t* pairs, int64_t n_pairs, float* dist_host) {
+    if (!dist_host && n_frames > 0) return fail(CV_E_INVALID, "null output");
+    CvPlanDesc d{};
+    d.struct_size = sizeof(CvPlanDesc);
+    d.n_atoms = n_atoms; d.n_pairs = n_pairs; d.pairs = pairs;
+    d.n_triplets = 0; d.triplets = nullptr;
+    d.box_kind = CV_BOX_NONE;
+    d.pair_cutoff = 0.0; d.hbond_dist_cutoff = 0.0; d.hbond_angle_cutoff = 0.0;
+    d.device = -1;
+    CvPlan* plan = nullptr;
+    int rc = caviar_plan_create(&d, &plan);
+    if (rc != CV_OK) return rc;
+    CvHostOutputs o{};
+    o.dist = dist_host;
+    rc = caviar_features_host(plan, xyz_host, 3ll * n_atoms, nullptr, n_frames, &o, 0);
+    caviar_plan_destroy(plan);
+    return rc;
+}

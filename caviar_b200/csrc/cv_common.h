@@ -1,0 +1,73 @@
+// Shared host/device definitions of the CAVIAR pair-feature path (sm_100a).
+#pragma once
+#include <stdint.h>
+
+namespace cv {
+
+constexpr int kConsumerThreads = 256;   // 8 warps evaluate features
+constexpr int kProducerThreads = 32;    // 1 warp drives the TMA pipeline (staged / zero-copy modes)
+constexpr int kFeatPerThread   = 4;     // features whose atom indices a thread keeps in registers
+constexpr int kTileWidth       = kConsumerThreads * kFeatPerThread;   // 1024 features per column tile
+constexpr int kMaxShifts       = 16;    // lattice translations the image search may have to try
+constexpr int kRecFloats       = 12 + 4 * kMaxShifts;                 // 76 floats = 304 B per frame
+constexpr int kMaxStages       = 8;
+constexpr int kMaxGroupAtoms   = 21840; // 3*atom offsets stay below 65536 floats (256 KB) -- smem bound anyway
+
+// box record layout (floats)
+enum : int {
+    REC_AX = 0, REC_BY = 1, REC_CZ = 2, REC_BX = 3, REC_CX = 4, REC_CY = 5,
+    REC_IAX = 6, REC_IBY = 7, REC_ICZ = 8, REC_RSAFE2 = 9, REC_NSHIFT = 10, REC_PAD = 11,
+    REC_SHIFTS = 12
+};
+
+enum : int { KIND_PAIR = 0, KIND_TRIPLET = 1 };
+
+// One column tile = a contiguous slice of features evaluated by one CTA at a time.
+struct TileDesc {
+    int32_t kind;        // KIND_PAIR / KIND_TRIPLET
+    int32_t f_begin;     // first feature, counted within its kind (multiple of 32)
+    int32_t n_feat;      // features in the tile (<= kTileWidth)
+    int32_t idx_off;     // first slot of the tile in the index tables (tile * kTileWidth)
+    int32_t grp_off;     // float offset of the tile's atom block inside one staged frame
+    int32_t grp_floats;  // floats of that block (multiple of 4)
+    int32_t n_slots;     // frame partitions (CTAs) sharing this tile = partial slots written
+    int32_t reserved;
+};
+
+// Static work assignment of one persistent CTA.
+struct CtaDesc {
+    int32_t tile_first;  // first tile
+    int32_t tile_step;   // stride to the next tile of this CTA (n_ctas when tiles outnumber CTAs)
+    int32_t r;           // frame partition index within the tile
+    int32_t R;           // number of frame partitions of the tile
+};
+
+struct RunParams {
+    const float* coords;        // staged buffer, or the caller's frames
+    long long    frame_stride;  // floats between consecutive frames of `coords`
+    const float* boxrec;        // kRecFloats per frame, or nullptr
+    long long    n_frames;
+    const TileDesc* tiles;
+    const CtaDesc*  ctas;
+    const int32_t*  idx0;       // per tile slot: 3*atom (float offset) of atom role 0 / 1 / 2
+    const int32_t*  idx1;
+    const int32_t*  idx2;
+    int32_t n_tiles;
+    int32_t frames_per_stage;
+    int32_t n_stages;
+    int32_t stage_floats;       // floats reserved per pipeline stage for coordinates
+    float*    dist;
+    float*    angle;
+    uint32_t* flags;
+    int32_t*  score;
+    long long P, A, W, Wp;      // pairs, triplets, flag words per frame, pair flag words
+    unsigned long long* occ_part;   // [slot][P+A]
+    double* sum_part;
+    double* sq_part;
+    float pair_thr;             // d < pair_thr
+    float hb_dthr;              // d(a,c) < hb_dthr
+    float hb_athr;              // angle > hb_athr
+    int32_t whole_frame;        // 1: a stage is frames_per_stage consecutive whole frames (one bulk copy)
+};
+
+}  // namespace cv

@@ -1,0 +1,266 @@
+// Host-side planning for the CAVIAR pair-feature path (pure C++, no CUDA calls).
+//
+// A plan cuts the feature list (pairs first, then triplets; column order = input order, CAVIAR-1.0.py:122)
+// into column tiles of <= 1024 features, decides how coordinates reach the SMs (direct gather / zero-copy TMA /
+// staged TMA), lays out the staged coordinate blocks, and assigns every persistent CTA one tile and a frame
+// partition so that pair indices stay in registers for the lifetime of the CTA.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/caviar_b200.h"
+#include "cv_common.h"
+
+namespace cv {
+
+struct HostPlan {
+    CvPlanDesc desc{};
+    std::vector<int32_t> pairs, triplets;
+    int mode = CV_MODE_DIRECT;
+    int n_sms = 148;
+    int occupancy = 2;
+    int n_ctas = 0;
+    int n_pair_tiles = 0, n_trip_tiles = 0, pair_tile_w = kTileWidth, trip_tile_w = kTileWidth;
+    std::vector<TileDesc> tiles;
+    std::vector<CtaDesc> ctas;
+    std::vector<int32_t> idx0, idx1, idx2;
+    std::vector<int32_t> src_off;      // staged float j of a frame <- float src_off[j] of the input frame
+    int64_t staged_floats = 0;
+    int64_t n_distinct = 0;
+    int frames_per_stage = 1, n_stages = 0, stage_floats = 0, smem_bytes = 0, whole_frame = 0;
+    int partial_slots = 1;
+    int64_t P = 0, A = 0, W = 0, Wp = 0;
+    float pair_thr = 0.f, hb_dthr = 0.f, hb_athr = 0.f;
+};
+
+inline float f32_at_or_above(double c) {     // smallest float t with (double)t >= c:  (double)d < c  <=>  d < t
+    if (std::isnan(c)) return -INFINITY;     // never true
+    float t = (float)c;
+    if ((double)t < c) t = std::nextafterf(t, INFINITY);
+    return t;
+}
+inline float f32_at_or_below(double c) {     // largest float t with (double)t <= c:  (double)a > c  <=>  a > t
+    if (std::isnan(c)) return INFINITY;
+    float t = (float)c;
+    if ((double)t > c) t = std::nextafterf(t, -INFINITY);
+    return t;
+}
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+inline void split_tiles(int64_t n, int& n_tiles, int& width) {
+    if (n <= 0) { n_tiles = 0; width = kTileWidth; return; }
+    int64_t c = (n + kTileWidth - 1) / kTileWidth;
+    int64_t w = (n + c - 1) / c;
+    width = round_up((int)w, 32);
+    n_tiles = (int)((n + width - 1) / width);
+}
+
+// Returns "" on success, otherwise the reason.
+inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
+    if (d.struct_size != sizeof(CvPlanDesc)) return "CvPlanDesc.struct_size mismatch (ABI)";
+    if (d.n_atoms <= 0) return "n_atoms must be positive";
+    if (d.n_pairs < 0 || d.n_triplets < 0) return "negative feature count";
+    if (d.n_pairs + d.n_triplets == 0) return "need at least one pair or triplet";
+    if ((d.n_pairs > 0 && !d.pairs) || (d.n_triplets > 0 && !d.triplets)) return "null index array";
+    if (d.box_kind < CV_BOX_NONE || d.box_kind > CV_BOX_TRICLINIC) return "unknown box_kind";
+    if ((long long)d.n_atoms * 3 >= (1ll << 31)) return "n_atoms too large";
+    if (d.n_pairs + d.n_triplets >= (1ll << 31) - kTileWidth) return "too many features";
+    hp.desc = d;
+    hp.P = d.n_pairs; hp.A = d.n_triplets;
+    hp.pairs.assign(d.pairs, d.pairs + 2 * d.n_pairs);
+    hp.triplets.assign(d.triplets, d.triplets + 3 * d.n_triplets);
+    hp.desc.pairs = nullptr; hp.desc.triplets = nullptr;
+    for (int32_t v : hp.pairs) if (v < 0 || v >= d.n_atoms) return "pair index out of range";
+    for (int32_t v : hp.triplets) if (v < 0 || v >= d.n_atoms) return "triplet index out of range";
+    hp.Wp = (hp.P + 31) / 32;
+    hp.W = hp.Wp + (hp.A + 31) / 32;
+    hp.pair_thr = f32_at_or_above(d.pair_cutoff);
+    hp.hb_dthr = f32_at_or_above(d.hbond_dist_cutoff);
+    hp.hb_athr = f32_at_or_below(d.hbond_angle_cutoff);
+    hp.n_sms = n_sms > 0 ? n_sms : 148;
+
+    split_tiles(hp.P, hp.n_pair_tiles, hp.pair_tile_w);
+    split_tiles(hp.A, hp.n_trip_tiles, hp.trip_tile_w);
+    const int C = hp.n_pair_tiles + hp.n_trip_tiles;
+    hp.tiles.resize(C);
+    for (int c = 0; c < C; ++c) {
+        TileDesc& t = hp.tiles[c];
+        const bool trip = c >= hp.n_pair_tiles;
+        const int ci = trip ? c - hp.n_pair_tiles : c;
+        const int w = trip ? hp.trip_tile_w : hp.pair_tile_w;
+        const int64_t n = trip ? hp.A : hp.P;
+        t.kind = trip ? KIND_TRIPLET : KIND_PAIR;
+        t.f_begin = ci * w;
+        t.n_feat = (int)std::min<int64_t>(w, n - (int64_t)ci * w);
+        t.idx_off = c * kTileWidth;
+        t.grp_off = 0; t.grp_floats = 0; t.n_slots = 1; t.reserved = 0;
+    }
+
+    // distinct atoms per tile and overall
+    std::vector<std::vector<int32_t>> tile_atoms(C);
+    std::vector<uint8_t> seen((size_t)d.n_atoms, 0);
+    int64_t sum_u = 0;
+    int max_u = 0;
+    for (int c = 0; c < C; ++c) {
+        const TileDesc& t = hp.tiles[c];
+        std::vector<int32_t>& a = tile_atoms[c];
+        if (t.kind == KIND_PAIR) a.assign(hp.pairs.begin() + 2ll * t.f_begin, hp.pairs.begin() + 2ll * (t.f_begin + t.n_feat));
+        else a.assign(hp.triplets.begin() + 3ll * t.f_begin, hp.triplets.begin() + 3ll * (t.f_begin + t.n_feat));
+        std::sort(a.begin(), a.end());
+        a.erase(std::unique(a.begin(), a.end()), a.end());
+        for (int32_t v : a) seen[v] = 1;
+        sum_u += (int64_t)a.size();
+        max_u = std::max(max_u, (int)a.size());
+    }
+    hp.n_distinct = 0;
+    for (uint8_t s : seen) hp.n_distinct += s;
+
+    // ---- how do coordinates reach the SMs? ----
+    const int64_t frame_bytes = 12ll * d.n_atoms;
+    const bool zc_ok = (d.n_atoms % 4 == 0) && frame_bytes <= 48 * 1024;
+    if (d.flags & CV_PLAN_FORCE_DIRECT) hp.mode = CV_MODE_DIRECT;
+    else if (d.flags & CV_PLAN_FORCE_STAGED) hp.mode = CV_MODE_STAGED;
+    else if (zc_ok && (int64_t)C * d.n_atoms <= 2 * sum_u + 1024) hp.mode = CV_MODE_ZEROCOPY;
+    else hp.mode = CV_MODE_STAGED;
+
+    bool shared_group = false;
+    int64_t u_pad_all = (hp.n_distinct + 3) / 4 * 4;
+    if (hp.mode == CV_MODE_STAGED) {
+        // one shared block when the tiles overlap heavily and the whole selection fits a stage
+        shared_group = (sum_u > hp.n_distinct + hp.n_distinct / 2) && (12 * u_pad_all <= 48 * 1024);
+    }
+
+    // ---- index tables (float offsets = 3 * atom slot) and the staged layout ----
+    hp.idx0.assign((size_t)C * kTileWidth, 0);
+    hp.idx1.assign((size_t)C * kTileWidth, 0);
+    hp.idx2.assign((size_t)C * kTileWidth, 0);
+    hp.src_off.clear();
+    std::vector<int32_t> global_slot;
+    if (hp.mode == CV_MODE_STAGED && shared_group) {
+        global_slot.assign((size_t)d.n_atoms, -1);
+        int32_t k = 0, last = 0;
+        for (int32_t a = 0; a < d.n_atoms; ++a)
+            if (seen[a]) { global_slot[a] = k++; last = a; hp.src_off.insert(hp.src_off.end(), {3 * a, 3 * a + 1, 3 * a + 2}); }
+        for (; k < u_pad_all; ++k) hp.src_off.insert(hp.src_off.end(), {3 * last, 3 * last + 1, 3 * last + 2});
+    }
+    int max_grp_floats = 0;
+    for (int c = 0; c < C; ++c) {
+        TileDesc& t = hp.tiles[c];
+        const std::vector<int32_t>& ua = tile_atoms[c];
+        auto local = [&](int32_t atom) -> int32_t {
+            if (hp.mode != CV_MODE_STAGED) return 3 * atom;
+            if (shared_group) return 3 * global_slot[atom];
+            return 3 * (int32_t)(std::lower_bound(ua.begin(), ua.end(), atom) - ua.begin());
+        };
+        if (hp.mode == CV_MODE_STAGED && !shared_group) {
+            const int u_pad = round_up((int)ua.size(), 4);
+            t.grp_off = (int32_t)hp.src_off.size();
+            t.grp_floats = 3 * u_pad;
+            for (int k = 0; k < u_pad; ++k) {
+                int32_t a = ua[std::min<size_t>(k, ua.size() - 1)];
+                hp.src_off.insert(hp.src_off.end(), {3 * a, 3 * a + 1, 3 * a + 2});
+            }
+        } else if (hp.mode == CV_MODE_STAGED) {
+            t.grp_off = 0; t.grp_floats = (int32_t)(3 * u_pad_all);
+        } else {
+            t.grp_off = 0; t.grp_floats = 3 * d.n_atoms;
+        }
+        max_grp_floats = std::max(max_grp_floats, t.grp_floats);
+        for (int s = 0; s < t.n_feat; ++s) {
+            const size_t o = (size_t)t.idx_off + s;
+            const int64_t f = (int64_t)t.f_begin + s;
+            if (t.kind == KIND_PAIR) {
+                hp.idx0[o] = local(hp.pairs[2 * f]); hp.idx1[o] = local(hp.pairs[2 * f + 1]);
+            } else {
+                hp.idx0[o] = local(hp.triplets[3 * f]); hp.idx1[o] = local(hp.triplets[3 * f + 1]);
+                hp.idx2[o] = local(hp.triplets[3 * f + 2]);
+            }
+        }
+    }
+    hp.staged_floats = (hp.mode == CV_MODE_STAGED) ? (int64_t)hp.src_off.size() : 0;
+    hp.whole_frame = (hp.mode == CV_MODE_ZEROCOPY) || (hp.mode == CV_MODE_STAGED && shared_group);
+
+    // ---- pipeline geometry ----
+    if (hp.mode == CV_MODE_DIRECT) {
+        hp.frames_per_stage = 1; hp.n_stages = 0; hp.stage_floats = 0; hp.smem_bytes = 0; hp.occupancy = 2;
+    } else {
+        const int gb = max_grp_floats * 4;
+        const int rec_b = d.box_kind != CV_BOX_NONE ? kRecFloats * 4 : 0;
+        int fb = std::max(1, std::min(16, (28 * 1024) / std::max(gb, 1)));
+        if (hp.whole_frame && (d.n_atoms % 4 != 0 || hp.mode == CV_MODE_STAGED)) { /* staged blocks are padded: any fb */ }
+        const int stage_total = fb * (gb + rec_b);
+        const int bar_bytes = 2 * kMaxStages * 8;
+        int ns = (110 * 1024 - bar_bytes) / stage_total;
+        if (ns >= 3) { hp.occupancy = 2; ns = std::min(ns, 4); }
+        else {
+            hp.occupancy = 1;
+            ns = std::min(kMaxStages, (220 * 1024 - bar_bytes) / stage_total);
+            if (ns < 2) return "a column tile's coordinate block does not fit in shared memory";
+        }
+        hp.frames_per_stage = fb; hp.n_stages = ns; hp.stage_floats = fb * max_grp_floats;
+        hp.smem_bytes = ns * stage_total + bar_bytes;
+    }
+
+    // ---- static CTA assignment ----
+    hp.n_ctas = d.n_ctas > 0 ? d.n_ctas : hp.n_sms * hp.occupancy;
+    hp.ctas.clear();
+    if (C <= hp.n_ctas) {
+        std::vector<double> cost(C);
+        double total = 0;
+        for (int c = 0; c < C; ++c) {
+            const TileDesc& t = hp.tiles[c];
+            const double coord_b = (hp.mode == CV_MODE_DIRECT ? 40.0 * tile_atoms[c].size() : 4.0 * t.grp_floats);
+            cost[c] = coord_b + t.n_feat * (t.kind == KIND_TRIPLET ? 40.0 : 16.0);
+            total += cost[c];
+        }
+        std::vector<int> R(C);
+        std::vector<std::pair<double, int>> frac(C);
+        int used = 0;
+        for (int c = 0; c < C; ++c) {
+            double share = hp.n_ctas * cost[c] / total;
+            R[c] = std::max(1, (int)std::floor(share));
+            frac[c] = {share - std::floor(share), c};
+            used += R[c];
+        }
+        std::sort(frac.begin(), frac.end(), [](const auto& a, const auto& b) { return a.first > b.first || (a.first == b.first && a.second < b.second); });
+        for (int k = 0; used < hp.n_ctas; ++k) { R[frac[k % C].second]++; ++used; }
+        for (int k = C - 1; used > hp.n_ctas; k = (k + C - 1) % C)       // over-subscribed by the max(1,.) floor
+            if (R[frac[k].second] > 1) { R[frac[k].second]--; --used; }
+        int max_r = 0;
+        for (int c = 0; c < C; ++c) { hp.tiles[c].n_slots = R[c]; max_r = std::max(max_r, R[c]); }
+        for (int r = 0; r < max_r; ++r)
+            for (int c = 0; c < C; ++c)
+                if (r < R[c]) hp.ctas.push_back(CtaDesc{c, C /*one tile only*/, r, R[c]});
+        hp.partial_slots = max_r;
+        hp.n_ctas = (int)hp.ctas.size();
+    } else {
+        for (int i = 0; i < hp.n_ctas; ++i) hp.ctas.push_back(CtaDesc{i, hp.n_ctas, 0, 1});
+        hp.partial_slots = 1;
+    }
+    return "";
+}
+
+inline void fill_info(const HostPlan& hp, CvPlanInfo& info) {
+    info.mode = hp.mode;
+    info.n_tiles = (int)hp.tiles.size();
+    info.n_ctas = hp.n_ctas;
+    info.threads_per_cta = kConsumerThreads + (hp.mode == CV_MODE_DIRECT ? 0 : kProducerThreads);
+    info.stages = hp.n_stages;
+    info.frames_per_stage = hp.frames_per_stage;
+    info.smem_bytes = hp.smem_bytes;
+    info.partial_slots = hp.partial_slots;
+    info.n_features = hp.P + hp.A;
+    info.n_flag_words = hp.W;
+    info.n_distinct_atoms = hp.n_distinct;
+    info.staged_floats_per_frame = hp.staged_floats;
+    info.boxrec_floats_per_frame = hp.desc.box_kind != CV_BOX_NONE ? kRecFloats : 0;
+    info.workspace_bytes = (int64_t)hp.partial_slots * (hp.P + hp.A) * 24;
+    const int64_t box_b = hp.desc.box_kind == CV_BOX_NONE ? 0 : (hp.desc.box_kind == CV_BOX_ORTHO ? 12 : 36);
+    info.algorithmic_bytes_per_frame = 12 * hp.n_distinct + box_b + 4 * hp.P + 4 * hp.A + 4 * hp.W + 4;
+}
+
+}  // namespace cv

@@ -1,0 +1,38 @@
+"""Drop-in for ``compute_distances_parallel`` (CAVIAR-1.0.py:110-122, callers :337, :338, :671).
+
+Same name, signature, return layout ((T, P), column k <-> pairs[k]) and error behaviour as the reference;
+the body is one C-ABI call into the sm_100a kernels (H2D, fused kernel, D2H).  float32 results are
+bit-identical to the reference's ``np.linalg.norm(X[:, i] - X[:, j], axis=2)``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+from .features import _index_array
+
+
+def compute_distances_parallel(X_xyz, pairs, n_jobs=None, chunk_size=8000):
+    """(T, n, 3) coordinates and a sequence of (i, j) -> (T, P) distances.
+
+    ``n_jobs`` and ``chunk_size`` are accepted for signature compatibility and ignored: the reference's
+    joblib threads over 8000-pair chunks (CAVIAR-1.0.py:113,121) have no counterpart on the device.
+    Reference behaviour kept: negative indices wrap, out-of-range raises IndexError, an empty pair list
+    raises ValueError (np.concatenate of nothing), float64 input gives float64 output (evaluated in
+    float32 on the device -- the callers cast to float32 anyway, CAVIAR-1.0.py:337).
+    """
+    X = np.asarray(X_xyz)
+    if X.ndim != 3 or X.shape[2] != 3:
+        raise ValueError(f"X_xyz must be (T, n, 3), got {X.shape}")
+    if len(pairs) == 0:
+        raise ValueError("need at least one array to concatenate")
+    out_dtype = np.float64 if X.dtype == np.float64 else np.float32
+    T, n = X.shape[0], X.shape[1]
+    idx = _index_array(pairs, 2, n, "pairs")
+    Xc = np.ascontiguousarray(X, dtype=np.float32)
+    D = np.empty((T, len(idx)), dtype=np.float32)
+    check(_lib.lib.caviar_pair_distances_host(Xc.ctypes.data, T, n, idx.ctypes.data, len(idx), D.ctypes.data))
+    return D if out_dtype == np.float32 else D.astype(np.float64)

@@ -1,0 +1,291 @@
+"""Host-side mirror of the hot path: plans, device runs and the reference-facing host entry points.
+
+``FeaturePlan`` wraps the opaque ``CvPlan`` of the C-ABI (include/caviar_b200.h).  PyTorch is used only for
+device memory and streams; every computation happens in the sm_100a kernels behind the C-ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import (BOX_NONE, BOX_ORTHO, BOX_TRICLINIC, CvAggregates, CvFrameOutputs, CvHostOutputs, CvPlanDesc,
+                   CvPlanInfo, MODE_DIRECT, MODE_STAGED, MODE_ZEROCOPY, PLAN_FORCE_DIRECT, PLAN_FORCE_STAGED, check)
+
+_BOX_KINDS = {None: BOX_NONE, "none": BOX_NONE, "ortho": BOX_ORTHO, "orthorhombic": BOX_ORTHO,
+              "triclinic": BOX_TRICLINIC}
+_FORCE = {None: 0, "auto": 0, "direct": PLAN_FORCE_DIRECT, "staged": PLAN_FORCE_STAGED}
+
+# Cut-off defaults.  8.0 is the reference's cluster_cut_A (CAVIAR-1.0.py:62); the reference has no angle or
+# H-bond criterion, 3.0 A / 135 deg are cpptraj's `hbond` defaults and are an extension of ours.
+DEFAULT_PAIR_CUTOFF = 8.0
+DEFAULT_HBOND_DIST_CUTOFF = 3.0
+DEFAULT_HBOND_ANGLE_CUTOFF = 135.0
+
+
+def _index_array(rows, width: int, n_atoms: int, what: str) -> np.ndarray:
+    """(K, width) int32, C-contiguous; negative indices wrap like numpy fancy indexing (CAVIAR-1.0.py:118)."""
+    if rows is None:
+        return np.zeros((0, width), dtype=np.int32)
+    arr = np.asarray(rows)
+    if arr.size == 0:
+        return np.zeros((0, width), dtype=np.int32)
+    if arr.ndim != 2 or arr.shape[1] != width:
+        raise ValueError(f"{what} must have shape (K, {width}), got {arr.shape}")
+    if not np.issubdtype(arr.dtype, np.integer):
+        raise IndexError(f"{what} must be integers")
+    arr = arr.astype(np.int64, copy=True)
+    bad = (arr < -n_atoms) | (arr >= n_atoms)
+    if bad.any():
+        k = int(arr[bad][0])
+        raise IndexError(f"index {k} is out of bounds for axis 1 with size {n_atoms}")
+    arr[arr < 0] += n_atoms
+    return np.ascontiguousarray(arr, dtype=np.int32)
+
+
+def normalize_box(box, n_frames: int, kind: int) -> Optional[np.ndarray]:
+    """None | (3,) | (T,3) | (3,3) | (T,3,3) -> float32 (T,3) [ortho] or (T,9) [triclinic] as the C-ABI wants."""
+    if kind == BOX_NONE:
+        return None
+    if box is None:
+        raise ValueError("plan has a periodic box but no box was given")
+    b = np.asarray(box, dtype=np.float64)
+    if kind == BOX_ORTHO:
+        if b.shape == (3,):
+            b = np.broadcast_to(b, (n_frames, 3))
+        if b.shape != (n_frames, 3):
+            raise ValueError(f"orthorhombic box must be (3,) or ({n_frames}, 3), got {b.shape}")
+        return np.ascontiguousarray(b, dtype=np.float32)
+    if b.shape == (3, 3):
+        b = np.broadcast_to(b, (n_frames, 3, 3))
+    if b.shape == (n_frames, 9):
+        b = b.reshape(n_frames, 3, 3)
+    if b.shape != (n_frames, 3, 3):
+        raise ValueError(f"triclinic box must be (3,3) or ({n_frames}, 3, 3), got {b.shape}")
+    return np.ascontiguousarray(b.reshape(n_frames, 9), dtype=np.float32)
+
+
+@dataclass
+class FrameOutputs:
+    dist: object = None      # (T, P) float32
+    angle: object = None     # (T, A) float32, degrees
+    flags: object = None     # (T, W) packed bits (int32 storage on device, uint32 on host)
+    score: object = None     # (T,) int32
+
+
+@dataclass
+class Aggregates:
+    occupancy: object        # (P + A,) int64 (device) / uint64 (host)
+    sum: object              # (P + A,) float64
+    sumsq: object            # (P + A,) float64
+
+    def mean(self, n_frames: int):
+        return self.sum / float(n_frames)
+
+    def var(self, n_frames: int, ddof: int = 1):
+        """Per-feature variance from the running sums (CAVIAR-1.0.py:539-545 uses ddof=1)."""
+        m = self.sum / float(n_frames)
+        return (self.sumsq - n_frames * m * m) / float(n_frames - ddof)
+
+
+class FeaturePlan:
+    """Pair / triplet lists + cut-offs compiled into a persistent-kernel work plan on one GPU."""
+
+    def __init__(self, n_atoms: int, pairs=None, triplets=None, box: Optional[str] = None,
+                 pair_cutoff: float = DEFAULT_PAIR_CUTOFF, hbond_dist_cutoff: float = DEFAULT_HBOND_DIST_CUTOFF,
+                 hbond_angle_cutoff: float = DEFAULT_HBOND_ANGLE_CUTOFF, force: Optional[str] = None,
+                 device: Optional[int] = None, n_ctas: int = 0, describe_only_sms: Optional[int] = None):
+        self.n_atoms = int(n_atoms)
+        self.pairs = _index_array(pairs, 2, self.n_atoms, "pairs")
+        self.triplets = _index_array(triplets, 3, self.n_atoms, "triplets")
+        self.box_kind = _BOX_KINDS[box]
+        self.pair_cutoff = float(pair_cutoff)
+        self.hbond_dist_cutoff = float(hbond_dist_cutoff)
+        self.hbond_angle_cutoff = float(hbond_angle_cutoff)
+        self._handle = C.c_void_p()
+        desc = CvPlanDesc()
+        desc.struct_size = C.sizeof(CvPlanDesc)
+        desc.n_atoms = self.n_atoms
+        desc.n_pairs = len(self.pairs)
+        desc.pairs = self.pairs.ctypes.data if len(self.pairs) else None
+        desc.n_triplets = len(self.triplets)
+        desc.triplets = self.triplets.ctypes.data if len(self.triplets) else None
+        desc.box_kind = self.box_kind
+        desc.flags = _FORCE[force]
+        desc.pair_cutoff = self.pair_cutoff
+        desc.hbond_dist_cutoff = self.hbond_dist_cutoff
+        desc.hbond_angle_cutoff = self.hbond_angle_cutoff
+        desc.device = -1 if device is None else int(device)
+        desc.n_ctas = int(n_ctas)
+        info = CvPlanInfo()
+        if describe_only_sms is not None:      # host-only dry run (no CUDA): used by CPU tests
+            check(_lib.lib.caviar_plan_describe(C.byref(desc), int(describe_only_sms), C.byref(info)))
+        else:
+            check(_lib.lib.caviar_plan_create(C.byref(desc), C.byref(self._handle)))
+            check(_lib.lib.caviar_plan_info(self._handle, C.byref(info)))
+        self.info = info.as_dict()
+        self.P, self.A = len(self.pairs), len(self.triplets)
+        self.F = self.P + self.A
+        self.W = int(info.n_flag_words)
+        self.mode = int(info.mode)
+        self.device = device
+
+    # -- lifetime ---------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            _lib.lib.caviar_plan_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- device path ------------------------------------------------------------------------------
+    @staticmethod
+    def _stream_ptr():
+        import torch
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def prepare_box(self, box):
+        """Raw per-frame boxes (torch CUDA float32 (T,3) | (T,9) | (T,3,3)) -> box records (T, 76)."""
+        import torch
+        if self.box_kind == BOX_NONE:
+            return None
+        width = 3 if self.box_kind == BOX_ORTHO else 9
+        b = box.reshape(box.shape[0], -1).to(torch.float32).contiguous()
+        if b.shape[1] != width:
+            raise ValueError(f"box must have {width} floats per frame, got {b.shape[1]}")
+        rec = torch.empty((b.shape[0], int(self.info["boxrec_floats_per_frame"])), dtype=torch.float32, device=b.device)
+        check(_lib.lib.caviar_prepare_box(self._handle, b.data_ptr(), b.shape[0], rec.data_ptr(), self._stream_ptr()))
+        return rec
+
+    def stage(self, xyz, out=None):
+        """K0: (T, N, 3) CUDA float32 frames -> staged (T, S) layout.  Identity for non-staged plans."""
+        import torch
+        if self.mode != MODE_STAGED:
+            return xyz
+        if xyz.dtype != torch.float32 or not xyz.is_cuda:
+            raise TypeError("stage() wants a CUDA float32 tensor")
+        if xyz.dim() != 3 or xyz.shape[1] != self.n_atoms or xyz.shape[2] != 3 or xyz.stride(2) != 1 or xyz.stride(1) != 3:
+            raise ValueError(f"frames must be (T, {self.n_atoms}, 3) with contiguous atoms")
+        T = xyz.shape[0]
+        S = int(self.info["staged_floats_per_frame"])
+        if out is None:
+            out = torch.empty((T, S), dtype=torch.float32, device=xyz.device)
+        check(_lib.lib.caviar_stage_frames(self._handle, xyz.data_ptr(), xyz.stride(0) if T > 1 else 3 * self.n_atoms,
+                                           T, out.data_ptr(), self._stream_ptr()))
+        return out
+
+    def new_aggregates(self, device="cuda") -> Aggregates:
+        import torch
+        return Aggregates(torch.zeros(self.F, dtype=torch.int64, device=device),
+                          torch.zeros(self.F, dtype=torch.float64, device=device),
+                          torch.zeros(self.F, dtype=torch.float64, device=device))
+
+    def new_workspace(self, device="cuda"):
+        import torch
+        return torch.empty(max(int(self.info["workspace_bytes"]), 8), dtype=torch.uint8, device=device)
+
+    def alloc_outputs(self, n_frames: int, want: Sequence[str] = ("dist", "angle", "flags", "score"), device="cuda"):
+        import torch
+        o = FrameOutputs()
+        if "dist" in want and self.P:
+            o.dist = torch.empty((n_frames, self.P), dtype=torch.float32, device=device)
+        if "angle" in want and self.A:
+            o.angle = torch.empty((n_frames, self.A), dtype=torch.float32, device=device)
+        if "flags" in want:
+            o.flags = torch.empty((n_frames, self.W), dtype=torch.int32, device=device)
+        if "score" in want:
+            o.score = torch.empty((n_frames,), dtype=torch.int32, device=device)
+        return o
+
+    def run(self, coords, boxrec=None, out: Optional[FrameOutputs] = None, aggregates: Optional[Aggregates] = None,
+            workspace=None, n_frames: Optional[int] = None) -> FrameOutputs:
+        """The fused kernel over frames resident on the device (staged layout for staged plans).
+
+        Asynchronous on torch's current stream.  ``aggregates`` are accumulated into.
+        """
+        import torch
+        if coords.dtype != torch.float32 or not coords.is_cuda:
+            raise TypeError("run() wants a CUDA float32 tensor")
+        T = coords.shape[0] if n_frames is None else int(n_frames)
+        if self.mode == MODE_STAGED:
+            if coords.dim() != 2 or coords.shape[1] != self.info["staged_floats_per_frame"] or not coords.is_contiguous():
+                raise ValueError("staged plan: pass the tensor returned by stage()")
+            stride = coords.shape[1]
+        else:
+            if coords.dim() != 3 or coords.shape[1] != self.n_atoms or coords.shape[2] != 3 \
+                    or coords.stride(2) != 1 or coords.stride(1) != 3:
+                raise ValueError(f"frames must be (T, {self.n_atoms}, 3) with contiguous atoms")
+            stride = coords.stride(0) if coords.shape[0] > 1 else 3 * self.n_atoms
+        if out is None:
+            out = self.alloc_outputs(T, device=coords.device)
+        fo = CvFrameOutputs(*(None if t is None else t.data_ptr() for t in (out.dist, out.angle, out.flags, out.score)))
+        ag_ptr = None
+        ws_ptr = None
+        if aggregates is not None:
+            if workspace is None:
+                workspace = self.new_workspace(coords.device)
+            ag = CvAggregates(aggregates.occupancy.data_ptr(), aggregates.sum.data_ptr(), aggregates.sumsq.data_ptr())
+            ag_ptr = C.byref(ag)
+            ws_ptr = workspace.data_ptr()
+        check(_lib.lib.caviar_run(self._handle, coords.data_ptr(), stride,
+                                  None if boxrec is None else boxrec.data_ptr(), T,
+                                  C.byref(fo), ag_ptr, ws_ptr, self._stream_ptr()))
+        self.last_launches = int(_lib.lib.caviar_last_launch_count())
+        return out
+
+    # -- reference-facing host path ---------------------------------------------------------------
+    def features_host(self, xyz: np.ndarray, box=None, want: Sequence[str] = ("dist", "angle", "flags", "score", "agg"),
+                      frames_per_block: int = 0, out: Optional[dict] = None) -> dict:
+        """HOST arrays in, HOST arrays out (H2D, kernels, D2H inside).  ``xyz`` is (T, N, 3) float32."""
+        xyz = np.asarray(xyz)
+        if xyz.ndim != 3 or xyz.shape[1] != self.n_atoms or xyz.shape[2] != 3:
+            raise ValueError(f"coordinates must be (T, {self.n_atoms}, 3), got {xyz.shape}")
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        T = xyz.shape[0]
+        b = normalize_box(box, T, self.box_kind)
+        res = {} if out is None else out
+        if "dist" in want and self.P and "dist" not in res:
+            res["dist"] = np.empty((T, self.P), dtype=np.float32)
+        if "angle" in want and self.A and "angle" not in res:
+            res["angle"] = np.empty((T, self.A), dtype=np.float32)
+        if "flags" in want and "flags" not in res:
+            res["flags"] = np.empty((T, self.W), dtype=np.uint32)
+        if "score" in want and "score" not in res:
+            res["score"] = np.empty((T,), dtype=np.int32)
+        if "agg" in want:
+            res["occupancy"] = np.zeros(self.F, dtype=np.uint64)
+            res["sum"] = np.zeros(self.F, dtype=np.float64)
+            res["sumsq"] = np.zeros(self.F, dtype=np.float64)
+        ho = CvHostOutputs()
+        for name in ("dist", "angle", "flags", "score", "occupancy", "sum", "sumsq"):
+            arr = res.get(name)
+            if arr is not None:
+                if isinstance(arr, np.ndarray):
+                    setattr(ho, name, arr.ctypes.data)
+                else:                               # a pinned torch CPU tensor
+                    setattr(ho, name, arr.data_ptr())
+        check(_lib.lib.caviar_features_host(self._handle, xyz.ctypes.data, 3 * self.n_atoms,
+                                            None if b is None else b.ctypes.data, T, C.byref(ho), int(frames_per_block)))
+        self.last_launches = int(_lib.lib.caviar_last_launch_count())
+        return res
+
+
+def unpack_flags(words: np.ndarray, n_pairs: int, n_triplets: int):
+    """(T, W) uint32 words -> ((T, P) bool, (T, A) bool).  Pair words come first (include/caviar_b200.h)."""
+    w = np.ascontiguousarray(words).view(np.uint32)
+    wp = (n_pairs + 31) // 32
+    bits = np.unpackbits(w.view(np.uint8).reshape(w.shape[0], -1), axis=1, bitorder="little").astype(bool)
+    return bits[:, :n_pairs], bits[:, 32 * wp:32 * wp + n_triplets]

@@ -1,0 +1,178 @@
+/*
+ * caviar_b200.h -- C-ABI of the B200-native CAVIAR pair-feature hot path.
+ *
+ * This is the drop-in boundary.  Every entry point takes
+ * plain pointers and sizes; no torch / numpy / C++ types cross it.  All
+ * functions return 0 (CV_OK) or a negative CV_E* code and never throw; the
+ * message of the last failure on the calling thread is caviar_last_error().
+ *
+ * What each entry point replaces in the reference (/root/reference):
+ *
+ *   caviar_pair_distances_host   CAVIAR-1.0.py:110-122  compute_distances_parallel()
+ *                                (called at :337, :338, :671) -- host (T,n,3) f32
+ *                                in, host (T,P) f32 out, no PBC, bit-exact.
+ *   caviar_features_host         CAVIAR_Distances-Extractor.py:143,159 -- the
+ *                                `distance dNNNN selA selB` series the cpptraj
+ *                                subprocess evaluates per frame (imaging on),
+ *                                plus the north_star extensions (angles, flags,
+ *                                occupancy, scores).
+ *   caviar_run (aggregates)      CAVIAR-1.0.py:342,380,496,674,783 (per-pair
+ *                                mean over frames = sum/T), :539-545 (mean/var
+ *                                from sum, sum of squares), :186 (threshold).
+ *   caviar_stage_frames          CAVIAR-1.0.py:335-336,670  atom_slice(ca).xyz
+ *                                (the compaction of selected atoms).
+ *
+ * Ownership: the caller owns every buffer it passes.  The library keeps no
+ * pointer after a call returns, except inside the opaque CvPlan (device copies
+ * of the index tables and cut-offs), which lives until caviar_plan_destroy().
+ * A plan may be used from several streams at once as long as each stream has
+ * its own workspace.
+ */
+#ifndef CAVIAR_B200_H
+#define CAVIAR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CV_ABI_VERSION 1
+
+/* status codes */
+#define CV_OK              0
+#define CV_E_INVALID      -1   /* bad argument (null pointer, negative size, index out of range) */
+#define CV_E_CUDA         -2   /* a CUDA runtime call failed; see caviar_last_error() */
+#define CV_E_NO_DEVICE    -3   /* no CUDA device / wrong architecture: there is no CPU fallback */
+#define CV_E_UNSUPPORTED  -4   /* e.g. a cell too skewed for the image search */
+#define CV_E_NOMEM        -5
+
+/* periodic box kinds */
+#define CV_BOX_NONE       0    /* plain Euclidean distance (the reference's compute_distances_parallel) */
+#define CV_BOX_ORTHO      1    /* per frame 3 floats: edge lengths */
+#define CV_BOX_TRICLINIC  2    /* per frame 9 floats: rows = lattice vectors, lower triangular
+                                  (a along x, b in the xy plane -- the Amber/cpptraj setting) */
+
+/* plan flags */
+#define CV_PLAN_FORCE_DIRECT  1  /* never stage: gather straight from the caller's frames */
+#define CV_PLAN_FORCE_STAGED  2  /* always stage through the compaction kernel */
+
+/* kernel paths a plan can resolve to */
+#define CV_MODE_DIRECT    0    /* gather from global memory, any frame stride */
+#define CV_MODE_ZEROCOPY  1    /* TMA-stream the caller's frames as they are (small, aligned frames) */
+#define CV_MODE_STAGED    2    /* compaction kernel -> grouped layout -> TMA-streamed */
+
+typedef struct CvPlan CvPlan;
+
+typedef struct CvPlanDesc {
+    uint32_t struct_size;        /* sizeof(CvPlanDesc), for ABI evolution */
+    int32_t  n_atoms;            /* atoms per input frame (N) */
+    int64_t  n_pairs;            /* P */
+    const int32_t* pairs;        /* host, [P][2] atom indices in [0, N) */
+    int64_t  n_triplets;         /* A */
+    const int32_t* triplets;     /* host, [A][3] (a, b, c): angle at b, end distance a..c */
+    int32_t  box_kind;           /* CV_BOX_* */
+    int32_t  flags;              /* CV_PLAN_* */
+    double   pair_cutoff;        /* contact flag:  (double)d < pair_cutoff   (CAVIAR-1.0.py:186 semantics) */
+    double   hbond_dist_cutoff;  /* triplet flag:  (double)d(a,c) < hbond_dist_cutoff  and            */
+    double   hbond_angle_cutoff; /*                (double)angle_deg > hbond_angle_cutoff             */
+    int32_t  device;             /* CUDA device ordinal, -1 = current */
+    int32_t  n_ctas;             /* 0 = auto (SM count x resident CTAs) -- for tests */
+} CvPlanDesc;
+
+typedef struct CvPlanInfo {
+    int32_t  mode;                    /* CV_MODE_* */
+    int32_t  n_tiles;                 /* column tiles (feature slices handled by one CTA at a time) */
+    int32_t  n_ctas;                  /* persistent grid size */
+    int32_t  threads_per_cta;
+    int32_t  stages;                  /* TMA pipeline depth (0 in direct mode) */
+    int32_t  frames_per_stage;
+    int32_t  smem_bytes;              /* dynamic shared memory per CTA */
+    int32_t  partial_slots;           /* frame partitions whose partial aggregates are reduced */
+    int64_t  n_features;              /* P + A */
+    int64_t  n_flag_words;            /* ceil(P/32) + ceil(A/32) uint32 words per frame */
+    int64_t  n_distinct_atoms;        /* U */
+    int64_t  staged_floats_per_frame; /* floats per frame of the staged layout (0 unless CV_MODE_STAGED) */
+    int64_t  boxrec_floats_per_frame; /* floats per frame of a prepared box record */
+    int64_t  workspace_bytes;         /* caller-provided scratch for caviar_run */
+    int64_t  algorithmic_bytes_per_frame; /* 12U + box + 4P + 4A + 4*flag_words + 4 */
+} CvPlanInfo;
+
+/* Per-frame outputs of one caviar_run call (device pointers, any may be NULL). */
+typedef struct CvFrameOutputs {
+    float*    dist;    /* [n_frames][P]  row-major, column k <-> pairs[k] (CAVIAR-1.0.py:122) */
+    float*    angle;   /* [n_frames][A]  degrees */
+    uint32_t* flags;   /* [n_frames][n_flag_words]; pair words first, then triplet words;
+                          bit b of word w = feature 32*w + b of that kind */
+    int32_t*  score;   /* [n_frames] number of set flags in the frame */
+} CvFrameOutputs;
+
+/* Running per-feature aggregates (device pointers, all-or-none).  caviar_run ADDS
+ * the block's totals, so a trajectory processed in several blocks accumulates. */
+typedef struct CvAggregates {
+    uint64_t* occupancy;  /* [P + A] frames in which the flag was set */
+    double*   sum;        /* [P + A] sum over frames of d (pairs) / angle (triplets) */
+    double*   sumsq;      /* [P + A] sum of squares */
+} CvAggregates;
+
+/* Host-side planning only (no CUDA call): what plan_create would decide. */
+int caviar_plan_describe(const CvPlanDesc* desc, int32_t n_sms, CvPlanInfo* info);
+
+int  caviar_plan_create(const CvPlanDesc* desc, CvPlan** plan);
+void caviar_plan_destroy(CvPlan* plan);
+int  caviar_plan_info(const CvPlan* plan, CvPlanInfo* info);
+
+/* Raw boxes (device, float32: [T][3] ortho or [T][9] triclinic) -> per-frame box
+ * records (device, boxrec_floats_per_frame each): inverse edges, safe radius and
+ * the list of lattice translations the image search has to try. */
+int caviar_prepare_box(const CvPlan* plan, const float* box_dev, int64_t n_frames,
+                       float* boxrec_dev, void* stream);
+
+/* Compaction (CV_MODE_STAGED only): frames (device, frame t at xyz + t*stride
+ * floats, AoS xyz) -> staged layout (device, staged_floats_per_frame each). */
+int caviar_stage_frames(const CvPlan* plan, const float* xyz_dev, int64_t frame_stride_floats,
+                        int64_t n_frames, float* staged_dev, void* stream);
+
+/* The fused hot path over n_frames frames resident on the device.
+ *   coords: CV_MODE_STAGED -> the staged buffer; otherwise the frames themselves
+ *           (frame_stride_floats apart; CV_MODE_ZEROCOPY needs stride == 3*n_atoms).
+ *   boxrec: prepared records, NULL iff box_kind == CV_BOX_NONE.
+ * Launches on `stream` (a cudaStream_t) and returns without synchronising. */
+int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t frame_stride_floats,
+               const float* boxrec_dev, int64_t n_frames,
+               const CvFrameOutputs* out, const CvAggregates* agg,
+               void* workspace_dev, void* stream);
+
+/* Number of kernels the last caviar_run / *_host call on this thread launched. */
+int64_t caviar_last_launch_count(void);
+
+/* Reference-facing, HOST buffers in and out (pageable or pinned).  Streams the
+ * frames through pinned staging, double buffered.  Any output may be NULL.
+ *   box_host: NULL | [T][3] | [T][9] float32 according to the plan's box_kind.
+ *   aggregates are written (not accumulated) as host arrays of P + A entries. */
+typedef struct CvHostOutputs {
+    float*    dist;       /* [T][P] */
+    float*    angle;      /* [T][A] */
+    uint32_t* flags;      /* [T][n_flag_words] */
+    int32_t*  score;      /* [T] */
+    uint64_t* occupancy;  /* [P + A] */
+    double*   sum;        /* [P + A] */
+    double*   sumsq;      /* [P + A] */
+} CvHostOutputs;
+
+int caviar_features_host(const CvPlan* plan, const float* xyz_host, int64_t frame_stride_floats,
+                         const float* box_host, int64_t n_frames, const CvHostOutputs* out,
+                         int64_t frames_per_block /* 0 = auto */);
+
+/* compute_distances_parallel(X, pairs) in one call: builds a throw-away plan
+ * (no box, no cut-offs) and fills dist_host [T][P].  CAVIAR-1.0.py:110-122. */
+int caviar_pair_distances_host(const float* xyz_host, int64_t n_frames, int32_t n_atoms,
+                               const int32_t* pairs, int64_t n_pairs, float* dist_host);
+
+const char* caviar_last_error(void);
+int caviar_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAVIAR_B200_H */

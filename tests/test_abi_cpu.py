@@ -1,0 +1,82 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every declared symbol, and plans sensibly."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import __graft_entry__ as g
+    g.build()
+    import caviar_b200
+    return caviar_b200
+
+
+def test_header_symbols_all_exported(cb):
+    from caviar_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "caviar_b200.h")).read()
+    declared = set(re.findall(r"\b(caviar_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(_lib.lib, name)
+    assert _lib.lib.caviar_abi_version() == 1
+
+
+def test_no_cpu_fallback(cb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(cb.CaviarError) as e:
+        cb.FeaturePlan(10, [(0, 1)])
+    assert e.value.code == -3
+    with pytest.raises(cb.CaviarError):
+        cb.compute_distances_parallel(np.zeros((2, 4, 3), np.float32), [(0, 1)])
+
+
+def test_reference_error_behaviour_needs_no_gpu(cb):
+    x = np.zeros((2, 4, 3), np.float32)
+    with pytest.raises(ValueError):
+        cb.compute_distances_parallel(x, [])
+    with pytest.raises(IndexError):
+        cb.compute_distances_parallel(x, [(0, 4)])
+
+
+@pytest.mark.parametrize("cfg_id,mode", [(1, "staged"), (2, "staged"), (3, "staged"), (4, "zerocopy")])
+def test_plan_describe_configs(cb, cfg_id, mode):
+    from caviar_b200 import synthetic as syn
+    top = syn.make_topology(cfg_id)
+    plan = cb.FeaturePlan(top.cfg.n_atoms, top.pairs, top.triplets, box=top.cfg.box, describe_only_sms=148)
+    info = plan.info
+    assert info["mode_name"] == mode
+    P, A = len(top.pairs), len(top.triplets)
+    assert info["n_features"] == P + A
+    assert info["n_flag_words"] == (P + 31) // 32 + (A + 31) // 32
+    assert info["n_distinct_atoms"] == len(top.referenced)
+    box_b = {None: 0, "ortho": 12, "triclinic": 36}[top.cfg.box]
+    assert info["algorithmic_bytes_per_frame"] == 12 * len(top.referenced) + box_b + 4 * P + 4 * A + 4 * info["n_flag_words"] + 4
+    assert info["n_ctas"] <= 296 and info["smem_bytes"] <= 113 * 1024 * (2 if info["n_ctas"] <= 148 else 1)
+    if mode == "staged":
+        assert info["staged_floats_per_frame"] % 12 == 0
+        assert info["staged_floats_per_frame"] >= 3 * len(top.referenced)
+        assert info["staged_floats_per_frame"] <= 3 * (2 * P + 3 * A) + 12 * info["n_tiles"]
+
+
+def test_plan_forced_modes_and_direct(cb):
+    rng = np.random.default_rng(0)
+    pairs = rng.integers(0, 4096, size=(5000, 2))
+    for force, mode in (("direct", "direct"), ("staged", "staged"), (None, "staged")):
+        info = cb.FeaturePlan(4096, pairs, None, describe_only_sms=148, force=force).info
+        assert info["mode_name"] == mode
+
+
+def test_thresholds_match_double_compare():
+    """smallest float32 >= cut: d < t  <=>  (double)d < cut -- the CAVIAR-1.0.py:186 comparison."""
+    from oracle import caviar_oracle as orc
+    for cut in (3.5, 4.5, 8.0, 0.8, 135.0):
+        t = orc.f32_at_or_above(cut)
+        for d in (np.nextafter(np.float32(cut), np.float32(0)), np.float32(cut), np.nextafter(np.float32(cut), np.float32(1e9))):
+            assert (d < t) == (float(d) < cut)
