@@ -4,12 +4,12 @@
 
 namespace cv {
 
-constexpr int kConsumerThreads = 256;   // 8 warps evaluate features
+constexpr int kConsumerThreads = 224;   // 7 warps evaluate features (+1 producer warp = 8 warps: 2 per SM sub-partition)
 constexpr int kProducerThreads = 32;    // 1 warp drives the TMA pipeline (staged / zero-copy modes)
 constexpr int kFeatPerThread   = 4;     // features whose atom indices a thread keeps in registers
-constexpr int kTileWidth       = kConsumerThreads * kFeatPerThread;   // 1024 features per column tile
+constexpr int kTileWidth       = kConsumerThreads * kFeatPerThread;   // 896 features per column tile
 constexpr int kMaxShifts       = 16;    // lattice translations the image search may have to try
-constexpr int kRecFloats       = 12 + 4 * kMaxShifts;                 // 76 floats = 304 B per frame
+constexpr int kRecFloats       = 12 + 4 * kMaxShifts + kMaxShifts + 12;  // 104 floats = 416 B per frame
 constexpr int kMaxStages       = 8;
 constexpr int kMaxGroupAtoms   = 21840; // 3*atom offsets stay below 65536 floats (256 KB) -- smem bound anyway
 
@@ -17,7 +17,9 @@ constexpr int kMaxGroupAtoms   = 21840; // 3*atom offsets stay below 65536 float
 enum : int {
     REC_AX = 0, REC_BY = 1, REC_CZ = 2, REC_BX = 3, REC_CX = 4, REC_CY = 5,
     REC_IAX = 6, REC_IBY = 7, REC_ICZ = 8, REC_RSAFE2 = 9, REC_NSHIFT = 10, REC_PAD = 11,
-    REC_SHIFTS = 12
+    REC_SHIFTS = 12,                       // kMaxShifts x float4 {vx, vy, vz, |v|^2 / 2}
+    REC_COEF = REC_SHIFTS + 4 * kMaxShifts,  // kMaxShifts x int: (sa+2) | (sb+2)<<4 | (sc+2)<<8, v = sa*a + sb*b + sc*c
+    REC_DBL = REC_COEF + kMaxShifts        // 6 doubles: ax, by, cz, bx, cx, cy (8-byte aligned: 92 floats in)
 };
 
 enum : int { KIND_PAIR = 0, KIND_TRIPLET = 1 };

@@ -1,7 +1,7 @@
 // Host-side planning for the CAVIAR pair-feature path (pure C++, no CUDA calls).
 //
 // A plan cuts the feature list (pairs first, then triplets; column order = input order, CAVIAR-1.0.py:122)
-// into column tiles of <= 1024 features, decides how coordinates reach the SMs (direct gather / zero-copy TMA /
+// into column tiles of <= 896 features, decides how coordinates reach the SMs (direct gather / zero-copy TMA /
 // staged TMA), lays out the staged coordinate blocks, and assigns every persistent CTA one tile and a frame
 // partition so that pair indices stay in registers for the lifetime of the CTA.
 #pragma once

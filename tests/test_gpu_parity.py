@@ -136,9 +136,10 @@ def _check_features(cb, res, x, box, pairs, triplets, cuts, exact_dist=False):
     s1, s2 = orc.moment_sums(feats)
     np.testing.assert_allclose(res["sum"], s1, rtol=1e-12, atol=1e-9)
     np.testing.assert_allclose(res["sumsq"], s2, rtol=1e-12, atol=1e-9)
-    # the reference's per-pair time mean (CAVIAR-1.0.py:342) is float32-accumulated: 1e-6 relative
+    # the reference's per-pair time mean (CAVIAR-1.0.py:342) accumulates in float32 down a strided axis (no
+    # pairwise blocking), so IT carries ~T*eps/4 relative error; our fp64 sum is the accurate side.
     if P:
-        np.testing.assert_allclose(res["sum"][:P] / T, orc.pair_time_mean(res["dist"]), rtol=1e-6)
+        np.testing.assert_allclose(res["sum"][:P] / T, orc.pair_time_mean(res["dist"]), rtol=max(1e-6, 3e-8 * T))
     return int(near_p.sum() + near_t.sum())
 
 
