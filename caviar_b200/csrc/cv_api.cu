@@ -40,7 +40,6 @@ struct CvPlan {
     HostPlan hp;
     int device = 0;
     TileDesc* d_tiles = nullptr;
-    CtaDesc* d_ctas = nullptr;
     int32_t *d_idx0 = nullptr, *d_idx1 = nullptr, *d_idx2 = nullptr;
     int32_t* d_src_off = nullptr;
     int* d_err = nullptr;
@@ -67,7 +66,7 @@ static cudaError_t upload(T** dst, const std::vector<T>& src) {
 
 extern "C" void caviar_plan_destroy(CvPlan* plan) {
     if (!plan) return;
-    cudaFree(plan->d_tiles); cudaFree(plan->d_ctas);
+    cudaFree(plan->d_tiles);
     cudaFree(plan->d_idx0); cudaFree(plan->d_idx1); cudaFree(plan->d_idx2);
     cudaFree(plan->d_src_off); cudaFree(plan->d_err);
     delete plan;
@@ -93,7 +92,6 @@ extern "C" int caviar_plan_create(const CvPlanDesc* desc, CvPlan** out) {
     if (!why.empty()) { delete p; return fail(CV_E_INVALID, why); }
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = upload(&p->d_tiles, p->hp.tiles);
-    if (e == cudaSuccess) e = upload(&p->d_ctas, p->hp.ctas);
     if (e == cudaSuccess) e = upload(&p->d_idx0, p->hp.idx0);
     if (e == cudaSuccess) e = upload(&p->d_idx1, p->hp.idx1);
     if (e == cudaSuccess) e = upload(&p->d_idx2, p->hp.idx2);
@@ -193,7 +191,7 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
     if (hp.desc.box_kind != CV_BOX_NONE && !boxrec_dev) return fail(CV_E_INVALID, "plan has a box but boxrec is null");
     const bool want_agg = agg && (agg->occupancy || agg->sum || agg->sumsq);
     if (want_agg && !(agg->occupancy && agg->sum && agg->sumsq)) return fail(CV_E_INVALID, "aggregates are all-or-none");
-    if (want_agg && !workspace_dev) return fail(CV_E_INVALID, "aggregates need a workspace");
+    if (!workspace_dev) return fail(CV_E_INVALID, "null workspace (CvPlanInfo.workspace_bytes of device memory)");
     cudaStream_t st = (cudaStream_t)stream;
 
     RunParams rp{};
@@ -212,7 +210,7 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
         if ((reinterpret_cast<uintptr_t>(coords_dev) & 15) != 0) return fail(CV_E_INVALID, "coordinates must be 16-byte aligned for TMA");
         if (boxrec_dev && (reinterpret_cast<uintptr_t>(boxrec_dev) & 15) != 0) return fail(CV_E_INVALID, "box records must be 16-byte aligned");
     }
-    rp.tiles = plan->d_tiles; rp.ctas = plan->d_ctas;
+    rp.tiles = plan->d_tiles;
     rp.idx0 = plan->d_idx0; rp.idx1 = plan->d_idx1; rp.idx2 = plan->d_idx2;
     rp.n_tiles = (int)hp.tiles.size();
     rp.frames_per_stage = hp.frames_per_stage; rp.n_stages = hp.n_stages; rp.stage_floats = hp.stage_floats;
@@ -220,13 +218,24 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
     if (out) { rp.dist = out->dist; rp.angle = out->angle; rp.flags = out->flags; rp.score = out->score; }
     rp.P = hp.P; rp.A = hp.A; rp.W = hp.W; rp.Wp = hp.Wp;
     const long long F = hp.P + hp.A;
+    // frame chunks of the work queue: about kItemsPerCta items per CTA, whole pipeline stages each
+    {
+        const int64_t fb = hp.frames_per_stage;
+        int64_t cf = (n_frames + hp.max_chunks - 1) / hp.max_chunks;
+        cf = std::max<int64_t>(fb, (cf + fb - 1) / fb * fb);
+        if (cf > (1ll << 30)) return fail(CV_E_INVALID, "too many frames for one run: split the call");
+        rp.chunk_frames = (int32_t)cf;
+        rp.n_chunks = (int32_t)((n_frames + cf - 1) / cf);
+    }
+    rp.queue = reinterpret_cast<unsigned int*>(workspace_dev);
     if (want_agg) {
-        rp.occ_part = reinterpret_cast<unsigned long long*>(workspace_dev);
-        rp.sum_part = reinterpret_cast<double*>(rp.occ_part + (long long)hp.partial_slots * F);
-        rp.sq_part = rp.sum_part + (long long)hp.partial_slots * F;
+        rp.occ_part = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace_dev) + kQueueBytes);
+        rp.sum_part = reinterpret_cast<double*>(rp.occ_part + (long long)rp.n_chunks * F);
+        rp.sq_part = rp.sum_part + (long long)rp.n_chunks * F;
     }
     rp.pair_thr = hp.pair_thr; rp.hb_dthr = hp.hb_dthr; rp.hb_athr = hp.hb_athr;
 
+    CV_CUDA(cudaMemsetAsync(rp.queue, 0, sizeof(unsigned int), st));
     if (rp.score) CV_CUDA(cudaMemsetAsync(rp.score, 0, sizeof(int32_t) * n_frames, st));
 
     cudaError_t e;
@@ -243,8 +252,7 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
     g_launches += 1;
     if (want_agg) {
         const unsigned blocks = (unsigned)((F + 255) / 256);
-        finalize_kernel<<<blocks, 256, 0, st>>>(rp.occ_part, rp.sum_part, rp.sq_part, hp.P, hp.A, hp.pair_tile_w,
-                                                hp.trip_tile_w, hp.n_pair_tiles, plan->d_tiles,
+        finalize_kernel<<<blocks, 256, 0, st>>>(rp.occ_part, rp.sum_part, rp.sq_part, F, rp.n_chunks,
                                                 reinterpret_cast<unsigned long long*>(agg->occupancy), agg->sum, agg->sumsq);
         CV_CUDA(cudaGetLastError());
         g_launches += 1;
@@ -322,6 +330,7 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
     DevBuf ws, occ, sum, sq, box_all, rec_all;
     Stream s_up, s_run, s_down;
     CV_CUDA(s_up.create()); CV_CUDA(s_run.create()); CV_CUDA(s_down.create());
+    CV_CUDA(ws.alloc((size_t)kQueueBytes + (size_t)hp.max_chunks * F * 24));
     for (Set& s : set) {
         CV_CUDA(s.xyz.alloc((size_t)TB * frame_stride_floats * 4));
         CV_CUDA(s.staged.alloc(hp.mode == CV_MODE_STAGED ? (size_t)TB * hp.staged_floats * 4 : 0));
@@ -341,7 +350,6 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
         CV_CUDA(s.uploaded.create()); CV_CUDA(s.computed.create()); CV_CUDA(s.downloaded.create());
     }
     if (want_agg) {
-        CV_CUDA(ws.alloc((size_t)hp.partial_slots * F * 24));
         CV_CUDA(occ.alloc((size_t)F * 8)); CV_CUDA(sum.alloc((size_t)F * 8)); CV_CUDA(sq.alloc((size_t)F * 8));
         CV_CUDA(cudaMemsetAsync(occ.p, 0, (size_t)F * 8, s_run.s));
         CV_CUDA(cudaMemsetAsync(sum.p, 0, (size_t)F * 8, s_run.s));

@@ -32,16 +32,7 @@ struct TileDesc {
     int32_t idx_off;     // first slot of the tile in the index tables (tile * kTileWidth)
     int32_t grp_off;     // float offset of the tile's atom block inside one staged frame
     int32_t grp_floats;  // floats of that block (multiple of 4)
-    int32_t n_slots;     // frame partitions (CTAs) sharing this tile = partial slots written
-    int32_t reserved;
-};
-
-// Static work assignment of one persistent CTA.
-struct CtaDesc {
-    int32_t tile_first;  // first tile
-    int32_t tile_step;   // stride to the next tile of this CTA (n_ctas when tiles outnumber CTAs)
-    int32_t r;           // frame partition index within the tile
-    int32_t R;           // number of frame partitions of the tile
+    int32_t reserved[2];
 };
 
 struct RunParams {
@@ -50,7 +41,6 @@ struct RunParams {
     const float* boxrec;        // kRecFloats per frame, or nullptr
     long long    n_frames;
     const TileDesc* tiles;
-    const CtaDesc*  ctas;
     const int32_t*  idx0;       // per tile slot: 3*atom (float offset) of atom role 0 / 1 / 2
     const int32_t*  idx1;
     const int32_t*  idx2;
@@ -58,12 +48,15 @@ struct RunParams {
     int32_t frames_per_stage;
     int32_t n_stages;
     int32_t stage_floats;       // floats reserved per pipeline stage for coordinates
+    int32_t chunk_frames;       // frames per work item (multiple of frames_per_stage)
+    int32_t n_chunks;           // work items = n_chunks * n_tiles, chunk-major
+    unsigned int* queue;        // work counter, zeroed before the launch
     float*    dist;
     float*    angle;
     uint32_t* flags;
     int32_t*  score;
     long long P, A, W, Wp;      // pairs, triplets, flag words per frame, pair flag words
-    unsigned long long* occ_part;   // [slot][P+A]
+    unsigned long long* occ_part;   // [n_chunks][P+A]: every (chunk, tile) item writes its own row segment
     double* sum_part;
     double* sq_part;
     float pair_thr;             // d < pair_thr
@@ -71,5 +64,8 @@ struct RunParams {
     float hb_athr;              // angle > hb_athr
     int32_t whole_frame;        // 1: a stage is frames_per_stage consecutive whole frames (one bulk copy)
 };
+
+constexpr int kQueueBytes = 256;        // the work counter lives at the head of the caller's workspace
+constexpr int kItemsPerCta = 16;        // work items per CTA the chunking aims for (tail imbalance <= ~1/16)
 
 }  // namespace cv

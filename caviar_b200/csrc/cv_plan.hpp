@@ -25,13 +25,12 @@ struct HostPlan {
     int n_ctas = 0;
     int n_pair_tiles = 0, n_trip_tiles = 0, pair_tile_w = kTileWidth, trip_tile_w = kTileWidth;
     std::vector<TileDesc> tiles;
-    std::vector<CtaDesc> ctas;
     std::vector<int32_t> idx0, idx1, idx2;
     std::vector<int32_t> src_off;      // staged float j of a frame <- float src_off[j] of the input frame
     int64_t staged_floats = 0;
     int64_t n_distinct = 0;
     int frames_per_stage = 1, n_stages = 0, stage_floats = 0, smem_bytes = 0, whole_frame = 0;
-    int partial_slots = 1;
+    int max_chunks = 1;                // upper bound of frame chunks per run (sizes the workspace)
     int64_t P = 0, A = 0, W = 0, Wp = 0;
     float pair_thr = 0.f, hb_dthr = 0.f, hb_athr = 0.f;
 };
@@ -97,7 +96,7 @@ inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
         t.f_begin = ci * w;
         t.n_feat = (int)std::min<int64_t>(w, n - (int64_t)ci * w);
         t.idx_off = c * kTileWidth;
-        t.grp_off = 0; t.grp_floats = 0; t.n_slots = 1; t.reserved = 0;
+        t.grp_off = 0; t.grp_floats = 0; t.reserved[0] = t.reserved[1] = 0;
     }
 
     // distinct atoms per tile and overall
@@ -193,7 +192,7 @@ inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
         int fb = std::max(1, std::min(16, (28 * 1024) / std::max(gb, 1)));
         if (hp.whole_frame && (d.n_atoms % 4 != 0 || hp.mode == CV_MODE_STAGED)) { /* staged blocks are padded: any fb */ }
         const int stage_total = fb * (gb + rec_b);
-        const int bar_bytes = 2 * kMaxStages * 8;
+        const int bar_bytes = 2 * kMaxStages * 8 + kMaxStages * 24;   // mbarriers + per-stage work metadata
         int ns = (110 * 1024 - bar_bytes) / stage_total;
         if (ns >= 3) { hp.occupancy = 2; ns = std::min(ns, 4); }
         else {
@@ -205,42 +204,11 @@ inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
         hp.smem_bytes = ns * stage_total + bar_bytes;
     }
 
-    // ---- static CTA assignment ----
+    // ---- persistent grid + dynamic work queue ----
+    // CTAs pull (frame chunk, tile) items from an atomic counter; chunks are sized so that every CTA gets about
+    // kItemsPerCta items, which bounds the tail imbalance without inflating the partial-aggregate buffers.
     hp.n_ctas = d.n_ctas > 0 ? d.n_ctas : hp.n_sms * hp.occupancy;
-    hp.ctas.clear();
-    if (C <= hp.n_ctas) {
-        std::vector<double> cost(C);
-        double total = 0;
-        for (int c = 0; c < C; ++c) {
-            const TileDesc& t = hp.tiles[c];
-            const double coord_b = (hp.mode == CV_MODE_DIRECT ? 40.0 * tile_atoms[c].size() : 4.0 * t.grp_floats);
-            cost[c] = coord_b + t.n_feat * (t.kind == KIND_TRIPLET ? 40.0 : 16.0);
-            total += cost[c];
-        }
-        std::vector<int> R(C);
-        std::vector<std::pair<double, int>> frac(C);
-        int used = 0;
-        for (int c = 0; c < C; ++c) {
-            double share = hp.n_ctas * cost[c] / total;
-            R[c] = std::max(1, (int)std::floor(share));
-            frac[c] = {share - std::floor(share), c};
-            used += R[c];
-        }
-        std::sort(frac.begin(), frac.end(), [](const auto& a, const auto& b) { return a.first > b.first || (a.first == b.first && a.second < b.second); });
-        for (int k = 0; used < hp.n_ctas; ++k) { R[frac[k % C].second]++; ++used; }
-        for (int k = C - 1; used > hp.n_ctas; k = (k + C - 1) % C)       // over-subscribed by the max(1,.) floor
-            if (R[frac[k].second] > 1) { R[frac[k].second]--; --used; }
-        int max_r = 0;
-        for (int c = 0; c < C; ++c) { hp.tiles[c].n_slots = R[c]; max_r = std::max(max_r, R[c]); }
-        for (int r = 0; r < max_r; ++r)
-            for (int c = 0; c < C; ++c)
-                if (r < R[c]) hp.ctas.push_back(CtaDesc{c, C /*one tile only*/, r, R[c]});
-        hp.partial_slots = max_r;
-        hp.n_ctas = (int)hp.ctas.size();
-    } else {
-        for (int i = 0; i < hp.n_ctas; ++i) hp.ctas.push_back(CtaDesc{i, hp.n_ctas, 0, 1});
-        hp.partial_slots = 1;
-    }
+    hp.max_chunks = std::max(1, (kItemsPerCta * hp.n_ctas + C - 1) / C);
     return "";
 }
 
@@ -252,13 +220,13 @@ inline void fill_info(const HostPlan& hp, CvPlanInfo& info) {
     info.stages = hp.n_stages;
     info.frames_per_stage = hp.frames_per_stage;
     info.smem_bytes = hp.smem_bytes;
-    info.partial_slots = hp.partial_slots;
+    info.partial_slots = hp.max_chunks;
     info.n_features = hp.P + hp.A;
     info.n_flag_words = hp.W;
     info.n_distinct_atoms = hp.n_distinct;
     info.staged_floats_per_frame = hp.staged_floats;
     info.boxrec_floats_per_frame = hp.desc.box_kind != CV_BOX_NONE ? kRecFloats : 0;
-    info.workspace_bytes = (int64_t)hp.partial_slots * (hp.P + hp.A) * 24;
+    info.workspace_bytes = kQueueBytes + (int64_t)hp.max_chunks * (hp.P + hp.A) * 24;
     const int64_t box_b = hp.desc.box_kind == CV_BOX_NONE ? 0 : (hp.desc.box_kind == CV_BOX_ORTHO ? 12 : 36);
     info.algorithmic_bytes_per_frame = 12 * hp.n_distinct + box_b + 4 * hp.P + 4 * hp.A + 4 * hp.W + 4;
 }

@@ -233,13 +233,14 @@ class FeaturePlan:
             out = self.alloc_outputs(T, device=coords.device)
         fo = CvFrameOutputs(*(None if t is None else t.data_ptr() for t in (out.dist, out.angle, out.flags, out.score)))
         ag_ptr = None
-        ws_ptr = None
+        if workspace is None:      # work queue + partial aggregates; one cached buffer per plan (single-stream use)
+            if getattr(self, "_ws", None) is None or self._ws.device != coords.device:
+                self._ws = self.new_workspace(coords.device)
+            workspace = self._ws
+        ws_ptr = workspace.data_ptr()
         if aggregates is not None:
-            if workspace is None:
-                workspace = self.new_workspace(coords.device)
             ag = CvAggregates(aggregates.occupancy.data_ptr(), aggregates.sum.data_ptr(), aggregates.sumsq.data_ptr())
             ag_ptr = C.byref(ag)
-            ws_ptr = workspace.data_ptr()
         check(_lib.lib.caviar_run(self._handle, coords.data_ptr(), stride,
                                   None if boxrec is None else boxrec.data_ptr(), T,
                                   C.byref(fo), ag_ptr, ws_ptr, self._stream_ptr()))
