@@ -83,6 +83,8 @@ SYMBOLS = {
 
 
 def _load():
+    global LIB_PATH
+    LIB_PATH = os.environ.get("CAVIAR_B200_LIB", LIB_PATH)      # A/B testing of alternative builds
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} is missing. caviar_b200 has no CPU or PyTorch fallback: build the sm_100a library first "

@@ -36,6 +36,63 @@ extern "C" int64_t caviar_last_launch_count(void) { return g_launches; }
 // ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
+namespace {
+struct DevBuf {                       // grow-only device buffer
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t alloc(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+struct PinBuf {                       // grow-only pinned host buffer
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t alloc(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+struct Stream {
+    cudaStream_t s = nullptr;
+    cudaError_t create() { return s ? cudaSuccess : cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking); }
+    ~Stream() { if (s) cudaStreamDestroy(s); }
+};
+struct Event {
+    cudaEvent_t e = nullptr;
+    cudaError_t create() { return e ? cudaSuccess : cudaEventCreateWithFlags(&e, cudaEventDisableTiming); }
+    ~Event() { if (e) cudaEventDestroy(e); }
+};
+bool is_pinned(const void* p) {
+    if (!p) return true;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+// Everything caviar_features_host needs between calls: allocated on first use, grown on demand, freed with the plan.
+struct HostSet {
+    DevBuf xyz, staged, dist, angle, flags, score;
+    PinBuf h_in, h_dist, h_angle, h_flags, h_score;
+    Event uploaded, computed, downloaded;
+};
+struct HostCtx {
+    HostSet set[2];
+    DevBuf ws, occ, sum, sq, box_all, rec_all;
+    Stream s_up, s_run, s_down;
+    std::mutex mu;
+};
+}  // namespace
+
 struct CvPlan {
     HostPlan hp;
     int device = 0;
@@ -43,7 +100,7 @@ struct CvPlan {
     int32_t *d_idx0 = nullptr, *d_idx1 = nullptr, *d_idx2 = nullptr;
     int32_t* d_src_off = nullptr;
     int* d_err = nullptr;
-    std::once_flag smem_once;
+    mutable HostCtx host;     // cached resources of the host entry point
 };
 
 extern "C" int caviar_plan_describe(const CvPlanDesc* desc, int32_t n_sms, CvPlanInfo* info) {
@@ -263,36 +320,6 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
 // ------------------------------------------------------------------------------------------------
 // reference-facing host entry points
 // ------------------------------------------------------------------------------------------------
-namespace {
-struct DevBuf {
-    void* p = nullptr;
-    cudaError_t alloc(size_t bytes) { return bytes ? cudaMalloc(&p, bytes) : cudaSuccess; }
-    ~DevBuf() { if (p) cudaFree(p); }
-    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
-};
-struct PinBuf {
-    void* p = nullptr;
-    cudaError_t alloc(size_t bytes) { return bytes ? cudaMallocHost(&p, bytes) : cudaSuccess; }
-    ~PinBuf() { if (p) cudaFreeHost(p); }
-    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
-};
-struct Stream {
-    cudaStream_t s = nullptr;
-    cudaError_t create() { return cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking); }
-    ~Stream() { if (s) cudaStreamDestroy(s); }
-};
-struct Event {
-    cudaEvent_t e = nullptr;
-    cudaError_t create() { return cudaEventCreateWithFlags(&e, cudaEventDisableTiming); }
-    ~Event() { if (e) cudaEventDestroy(e); }
-};
-bool is_pinned(const void* p) {
-    if (!p) return true;
-    cudaPointerAttributes a{};
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeHost;
-}
-}  // namespace
 
 // Block loop with two device buffer sets: while block b computes, block b+1 is uploaded and block b-1 is
 // downloaded.  Pageable host memory goes through pinned bounce buffers (one memcpy each way); memory the
@@ -322,13 +349,12 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
     const bool in_pinned = is_pinned(xyz_host);
     const bool out_pinned = is_pinned(out->dist) && is_pinned(out->angle) && is_pinned(out->flags) && is_pinned(out->score);
 
-    struct Set {
-        DevBuf xyz, staged, dist, angle, flags, score;
-        PinBuf h_in, h_dist, h_angle, h_flags, h_score;
-        Event uploaded, computed, downloaded;
-    } set[2];
-    DevBuf ws, occ, sum, sq, box_all, rec_all;
-    Stream s_up, s_run, s_down;
+    HostCtx& hc = plan->host;
+    std::lock_guard<std::mutex> lock(hc.mu);           // one host call per plan at a time
+    HostSet (&set)[2] = hc.set;
+    DevBuf &ws = hc.ws, &occ = hc.occ, &sum = hc.sum, &sq = hc.sq, &box_all = hc.box_all, &rec_all = hc.rec_all;
+    Stream &s_up = hc.s_up, &s_run = hc.s_run, &s_down = hc.s_down;
+    typedef HostSet Set;
     CV_CUDA(s_up.create()); CV_CUDA(s_run.create()); CV_CUDA(s_down.create());
     CV_CUDA(ws.alloc((size_t)kQueueBytes + (size_t)hp.max_chunks * F * 24));
     for (Set& s : set) {

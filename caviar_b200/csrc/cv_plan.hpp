@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -193,13 +194,19 @@ inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
         if (hp.whole_frame && (d.n_atoms % 4 != 0 || hp.mode == CV_MODE_STAGED)) { /* staged blocks are padded: any fb */ }
         const int stage_total = fb * (gb + rec_b);
         const int bar_bytes = 2 * kMaxStages * 8 + kMaxStages * 24;   // mbarriers + per-stage work metadata
-        int ns = (110 * 1024 - bar_bytes) / stage_total;
-        if (ns >= 3) { hp.occupancy = 2; ns = std::min(ns, 4); }
-        else {
-            hp.occupancy = 1;
-            ns = std::min(kMaxStages, (220 * 1024 - bar_bytes) / stage_total);
-            if (ns < 2) return "a column tile's coordinate block does not fit in shared memory";
+        // resident CTAs per SM: 3 when two stages fit in a third of the shared memory (more warps hide the
+        // dependent-issue latency of the image search), else 2, else 1.  CAVIAR_OCC overrides (experiments).
+        int want_occ = 2;
+        if (const char* e = std::getenv("CAVIAR_OCC")) want_occ = std::max(1, std::min(3, atoi(e)));
+        int ns = 0;
+        hp.occupancy = 0;
+        const int budget[4] = {0, 220 * 1024, 110 * 1024, 73 * 1024};
+        const int min_stages[4] = {0, 2, 3, 2};
+        for (int occ = want_occ; occ >= 1 && hp.occupancy == 0; --occ) {
+            const int n = (budget[occ] - bar_bytes) / stage_total;
+            if (n >= min_stages[occ]) { hp.occupancy = occ; ns = std::min(n, occ == 1 ? kMaxStages : 4); }
         }
+        if (hp.occupancy == 0) return "a column tile's coordinate block does not fit in shared memory";
         hp.frames_per_stage = fb; hp.n_stages = ns; hp.stage_floats = fb * max_grp_floats;
         hp.smem_bytes = ns * stage_total + bar_bytes;
     }
