@@ -77,6 +77,8 @@ SYMBOLS = {
     "caviar_features_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                        C.POINTER(CvHostOutputs), C.c_int64]),
     "caviar_pair_distances_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
+    "caviar_format_csv": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+                                      C.c_void_p, C.c_int64]),
     "caviar_last_error": (C.c_char_p, []),
     "caviar_abi_version": (C.c_int, []),
 }
@@ -88,7 +90,7 @@ def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} is missing. caviar_b200 has no CPU or PyTorch fallback: build the sm_100a library first "
-            "(python -c 'import __graft_entry__ as g; g.build()'  or  python -m caviar_b200.build).")
+            "(python -c 'import __graft_entry__ as g; g.build()'  or  python caviar_b200/build.py).")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)          # AttributeError here = header and library out of sync

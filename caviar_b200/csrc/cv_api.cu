@@ -4,7 +4,9 @@
 
 #include <cstdio>
 #include <cstring>
+#include <cmath>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -484,4 +486,72 @@ extern "C" int caviar_pair_distances_host(const float* xyz_host, int64_t n_frame
     rc = caviar_features_host(plan, xyz_host, 3ll * n_atoms, nullptr, n_frames, &o, 0);
     caviar_plan_destroy(plan);
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CSV rows (host): fixed-point formatting without printf
+// ------------------------------------------------------------------------------------------------
+namespace {
+inline char* put_u64(char* p, unsigned long long v) {
+    char tmp[24];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+// "%.{dec}f" of a float.  (double)v * 10^dec is exact for dec <= 8 (24 + 27 bits < 53), and nearbyint() rounds
+// half-to-even exactly like printf does on the exact binary value.
+inline char* put_fixed(char* p, float v, int dec, double scale) {
+    if (!(std::fabs(v) < 1e15f) || dec > 8) return p + snprintf(p, 48, "%.*f", dec, (double)v);
+    double x = std::nearbyint(std::fabs((double)v) * scale);
+    unsigned long long q = (unsigned long long)x;
+    if (std::signbit(v) && q != 0) *p++ = '-';
+    else if (std::signbit(v) && q == 0) *p++ = '-';      // printf prints "-0.0000" for small negatives as well
+    unsigned long long ip = q, fp = 0, pw = 1;
+    for (int i = 0; i < dec; ++i) pw *= 10;
+    ip = q / pw; fp = q % pw;
+    p = put_u64(p, ip);
+    if (dec > 0) {
+        *p++ = '.';
+        for (unsigned long long d = pw / 10; d; d /= 10) *p++ = (char)('0' + (fp / d) % 10);
+    }
+    return p;
+}
+}  // namespace
+
+extern "C" int64_t caviar_format_csv(const float* values, int64_t rows, int64_t cols, int64_t row_stride_floats,
+                                     int64_t first_index, int64_t index_step, int32_t decimals, char* out, int64_t cap) {
+    if (rows < 0 || cols < 0 || decimals < 0 || decimals > 17) return fail(CV_E_INVALID, "bad csv shape");
+    if (rows == 0) return 0;
+    if (!values || !out) return fail(CV_E_INVALID, "null argument");
+    const int64_t per_row = 24 + 48 * cols;                    // worst case of one row
+    const double scale = std::pow(10.0, decimals);
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(hw ? hw : 4, 32), rows * cols / 65536 + 1));
+    std::vector<std::string> parts(nt);
+    std::vector<std::thread> pool;
+    auto work = [&](int k) {
+        const int64_t r0 = rows * k / nt, r1 = rows * (k + 1) / nt;
+        std::string& buf = parts[k];
+        buf.resize((size_t)((r1 - r0) * per_row));
+        char* p = &buf[0];
+        for (int64_t r = r0; r < r1; ++r) {
+            long long idx = first_index + r * index_step;
+            if (idx < 0) { *p++ = '-'; idx = -idx; }
+            p = put_u64(p, (unsigned long long)idx);
+            const float* row = values + r * row_stride_floats;
+            for (int64_t c = 0; c < cols; ++c) { *p++ = ','; p = put_fixed(p, row[c], decimals, scale); }
+            *p++ = '\n';
+        }
+        buf.resize((size_t)(p - &buf[0]));
+    };
+    for (int k = 1; k < nt; ++k) pool.emplace_back(work, k);
+    work(0);
+    for (auto& t : pool) t.join();
+    int64_t total = 0;
+    for (auto& b : parts) total += (int64_t)b.size();
+    if (total > cap) return fail(CV_E_NOMEM, "csv buffer too small");
+    char* o = out;
+    for (auto& b : parts) { memcpy(o, b.data(), b.size()); o += b.size(); }
+    return total;
 }

@@ -1,0 +1,252 @@
+"""Trajectory / topology ingest for the Extractor drop-in.
+
+The reference hands ``--top`` / ``--traj`` to the external cpptraj binary (CAVIAR_Distances-Extractor.py:120-125).
+Here the two formats that workflow uses are read directly:
+
+* Amber NetCDF trajectories (``.nc``; NetCDF-3, 64-bit offset): ``coordinates (frame, atom, 3)`` float32 Angstrom,
+  ``cell_lengths`` / ``cell_angles (frame, 3)`` float64 -- through ``scipy.io.netcdf_file(mmap=True)``, so frame
+  blocks are paged in on demand and never copied as a whole;
+* Amber prmtop topologies (``%FLAG ATOM_NAME / RESIDUE_LABEL / RESIDUE_POINTER``) and PDB files, only as far as
+  the ``:{idx}@CA`` / ``resid {n}@CA`` selections of the reference need (Extractor:127-138).
+
+A ``.npy`` array ``(T, N, 3)`` is accepted as a trajectory too (no box), which is what the tests and benchmarks use
+when no NetCDF file is at hand.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import numpy as np
+
+
+# ---------------------------------------------------------------------------------------------------------
+# topology
+# ---------------------------------------------------------------------------------------------------------
+@dataclass
+class Topology:
+    atom_names: List[str]
+    res_labels: List[str]           # per residue
+    res_first_atom: List[int]       # 0-based index of each residue's first atom
+    res_seq: Optional[List[int]]    # PDB resSeq per residue (None for prmtop)
+
+    @property
+    def n_atoms(self) -> int:
+        return len(self.atom_names)
+
+    @property
+    def n_res(self) -> int:
+        return len(self.res_labels)
+
+    def atom_of(self, res_index0: int, atom_name: str = "CA") -> int:
+        """0-based atom index of ``atom_name`` in residue ``res_index0`` (0-based); -1 when the residue has none."""
+        lo = self.res_first_atom[res_index0]
+        hi = self.res_first_atom[res_index0 + 1] if res_index0 + 1 < self.n_res else self.n_atoms
+        for a in range(lo, hi):
+            if self.atom_names[a] == atom_name:
+                return a
+        return -1
+
+    def residue_by_resseq(self, resseq: int) -> int:
+        if self.res_seq is None:
+            raise ValueError("this topology has no PDB residue numbers (resSeq needs a PDB topology)")
+        try:
+            return self.res_seq.index(resseq)
+        except ValueError:
+            return -1
+
+
+def _prmtop_sections(path: str) -> Dict[str, List[str]]:
+    sections: Dict[str, List[str]] = {}
+    name, fmt = None, None
+    with open(path, "r", errors="ignore") as fh:
+        for line in fh:
+            if line.startswith("%FLAG"):
+                name = line.split()[1]
+                sections[name] = []
+                fmt = None
+            elif line.startswith("%FORMAT"):
+                fmt = line.strip()[8:-1]
+                sections.setdefault(name, []).append("%" + fmt)
+            elif name is not None and not line.startswith("%"):
+                sections[name].append(line.rstrip("\n"))
+    return sections
+
+
+def _fixed_width(lines: List[str]) -> List[str]:
+    """Split the data lines of one prmtop section according to its Fortran format (20a4, 10I8, 5E16.8)."""
+    fmt = lines[0][1:].lower()
+    import re
+    m = re.match(r"(\d+)([aie])(\d+)", fmt)
+    width = int(m.group(3)) if m else 4
+    out = []
+    for ln in lines[1:]:
+        out += [ln[i:i + width] for i in range(0, len(ln), width)]
+    return out
+
+
+def read_prmtop(path: str) -> Topology:
+    sec = _prmtop_sections(path)
+    for need in ("POINTERS", "ATOM_NAME", "RESIDUE_LABEL", "RESIDUE_POINTER"):
+        if need not in sec:
+            raise ValueError(f"{path}: not an Amber prmtop (missing %FLAG {need})")
+    ptr = [int(x) for x in _fixed_width(sec["POINTERS"]) if x.strip()]
+    natom, nres = ptr[0], ptr[11]
+    names = [x.strip() for x in _fixed_width(sec["ATOM_NAME"])][:natom]
+    labels = [x.strip() for x in _fixed_width(sec["RESIDUE_LABEL"])][:nres]
+    first = [int(x) - 1 for x in _fixed_width(sec["RESIDUE_POINTER"]) if x.strip()][:nres]
+    if len(names) != natom or len(labels) != nres or len(first) != nres:
+        raise ValueError(f"{path}: truncated prmtop")
+    return Topology(names, labels, first, None)
+
+
+def read_pdb(path: str) -> Topology:
+    names, labels, first, seqs = [], [], [], []
+    last = None
+    with open(path, "r", errors="ignore") as fh:
+        for line in fh:
+            if not (line.startswith("ATOM") or line.startswith("HETATM")):
+                continue
+            key = (line[21], line[22:27])
+            if key != last:
+                last = key
+                first.append(len(names))
+                labels.append(line[17:20].strip())
+                seqs.append(int(line[22:26]))
+            names.append(line[12:16].strip())
+    if not names:
+        raise ValueError(f"{path}: no ATOM records")
+    return Topology(names, labels, first, seqs)
+
+
+def read_topology(path: str) -> Topology:
+    ext = os.path.splitext(path)[1].lower()
+    if ext in (".pdb", ".ent"):
+        return read_pdb(path)
+    return read_prmtop(path)
+
+
+def write_prmtop(path: str, atom_names: List[str], res_labels: List[str], res_first_atom: List[int]) -> None:
+    """Minimal prmtop with the four sections read above (for tests and synthetic fixtures)."""
+    def block(flag, fmt, items, per, width, conv):
+        out = [f"%FLAG {flag}", f"%FORMAT({fmt})"]
+        for i in range(0, max(len(items), 1), per):
+            out.append("".join(conv(x, width) for x in items[i:i + per]))
+        return out
+    ptr = [0] * 31
+    ptr[0], ptr[11] = len(atom_names), len(res_labels)
+    lines = ["%VERSION  VERSION_STAMP = V0001.000  DATE = 01/01/26  00:00:00"]
+    lines += block("TITLE", "20a4", ["caviar_b200 synthetic"], 1, 80, lambda x, w: x.ljust(w))
+    lines += block("POINTERS", "10I8", ptr, 10, 8, lambda x, w: str(x).rjust(w))
+    lines += block("ATOM_NAME", "20a4", atom_names, 20, 4, lambda x, w: x.ljust(w)[:w])
+    lines += block("RESIDUE_LABEL", "20a4", res_labels, 20, 4, lambda x, w: x.ljust(w)[:w])
+    lines += block("RESIDUE_POINTER", "10I8", [i + 1 for i in res_first_atom], 10, 8, lambda x, w: str(x).rjust(w))
+    with open(path, "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# cell
+# ---------------------------------------------------------------------------------------------------------
+def cell_to_matrix(lengths: np.ndarray, angles_deg: np.ndarray) -> np.ndarray:
+    """(T,3) lengths + (T,3) angles [alpha, beta, gamma] -> (T,3,3), rows = lattice vectors, lower triangular
+    (a along x, b in the xy plane): the Amber / cpptraj setting."""
+    L = np.asarray(lengths, dtype=np.float64).reshape(-1, 3)
+    ang = np.deg2rad(np.asarray(angles_deg, dtype=np.float64).reshape(-1, 3))
+    ca, cb, cg, sg = np.cos(ang[:, 0]), np.cos(ang[:, 1]), np.cos(ang[:, 2]), np.sin(ang[:, 2])
+    h = np.zeros((L.shape[0], 3, 3))
+    h[:, 0, 0] = L[:, 0]
+    h[:, 1, 0] = L[:, 1] * cg
+    h[:, 1, 1] = L[:, 1] * sg
+    h[:, 2, 0] = L[:, 2] * cb
+    h[:, 2, 1] = L[:, 2] * (ca - cb * cg) / sg
+    h[:, 2, 2] = np.sqrt(np.maximum(L[:, 2] ** 2 - h[:, 2, 0] ** 2 - h[:, 2, 1] ** 2, 0.0))
+    h[np.abs(h) < 1e-12 * np.abs(h).max()] = 0.0
+    return h
+
+
+# ---------------------------------------------------------------------------------------------------------
+# trajectories
+# ---------------------------------------------------------------------------------------------------------
+class Trajectory:
+    """Random access to frame blocks: ``coords(lo, hi, stride)`` -> float32 (n, N, 3); ``cell(...)`` -> box or None."""
+
+    def __init__(self, path: str):
+        self.path = path
+        ext = os.path.splitext(path)[1].lower()
+        self._nc = None
+        if ext == ".npy":
+            self._xyz = np.load(path, mmap_mode="r")
+            if self._xyz.ndim != 3 or self._xyz.shape[2] != 3:
+                raise ValueError(f"{path}: expected a (T, N, 3) array")
+            self._len = self._ang = None
+        else:
+            from scipy.io import netcdf_file
+            self._nc = netcdf_file(path, "r", mmap=True)
+            if "coordinates" not in self._nc.variables:
+                raise ValueError(f"{path}: no 'coordinates' variable (not an Amber NetCDF trajectory)")
+            self._xyz = self._nc.variables["coordinates"]
+            self._len = self._nc.variables.get("cell_lengths")
+            self._ang = self._nc.variables.get("cell_angles")
+        self.n_frames, self.n_atoms = int(self._xyz.shape[0]), int(self._xyz.shape[1])
+
+    @property
+    def has_box(self) -> bool:
+        if self._len is None or self._ang is None or self.n_frames == 0:
+            return False
+        return bool(np.all(np.asarray(self._len[0]) > 0))
+
+    def box_kind(self) -> Optional[str]:
+        if not self.has_box:
+            return None
+        ang = np.asarray(self._ang[0], dtype=np.float64)
+        return "ortho" if np.allclose(ang, 90.0, atol=1e-6) else "triclinic"
+
+    def coords(self, lo: int, hi: int, stride: int = 1) -> np.ndarray:
+        return np.ascontiguousarray(self._xyz[lo:hi:stride], dtype=np.float32)
+
+    def cell(self, lo: int, hi: int, stride: int = 1):
+        kind = self.box_kind()
+        if kind is None:
+            return None
+        L = np.asarray(self._len[lo:hi:stride], dtype=np.float64)
+        if kind == "ortho":
+            return L.astype(np.float32)
+        return cell_to_matrix(L, np.asarray(self._ang[lo:hi:stride], dtype=np.float64)).astype(np.float32)
+
+    def close(self):
+        if self._nc is not None:
+            self._xyz = self._len = self._ang = None
+            try:
+                self._nc.close()
+            except Exception:
+                pass
+            self._nc = None
+
+
+def write_netcdf(path: str, xyz: np.ndarray, cell_lengths=None, cell_angles=None) -> None:
+    """Amber-convention NetCDF-3 (64-bit offset) trajectory; for tests and synthetic fixtures."""
+    from scipy.io import netcdf_file
+    xyz = np.asarray(xyz, dtype=np.float32)
+    T, N, _ = xyz.shape
+    nc = netcdf_file(path, "w", version=2)
+    nc.Conventions = "AMBER"
+    nc.ConventionVersion = "1.0"
+    nc.program = "caviar_b200"
+    nc.createDimension("frame", T)
+    nc.createDimension("spatial", 3)
+    nc.createDimension("atom", N)
+    v = nc.createVariable("coordinates", "f", ("frame", "atom", "spatial"))
+    v.units = "angstrom"
+    v[:] = xyz
+    if cell_lengths is not None:
+        nc.createDimension("cell_spatial", 3)
+        nc.createDimension("cell_angular", 3)
+        cl = nc.createVariable("cell_lengths", "d", ("frame", "cell_spatial"))
+        cl.units = "angstrom"
+        cl[:] = np.broadcast_to(np.asarray(cell_lengths, dtype=np.float64), (T, 3))
+        ca = nc.createVariable("cell_angles", "d", ("frame", "cell_angular"))
+        ca.units = "degree"
+        ca[:] = np.broadcast_to(np.asarray(cell_angles if cell_angles is not None else [90.0] * 3, dtype=np.float64), (T, 3))
+    nc.close()

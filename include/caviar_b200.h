@@ -169,6 +169,14 @@ int caviar_features_host(const CvPlan* plan, const float* xyz_host, int64_t fram
 int caviar_pair_distances_host(const float* xyz_host, int64_t n_frames, int32_t n_atoms,
                                const int32_t* pairs, int64_t n_pairs, float* dist_host);
 
+/* Host-side CSV row formatter for the Extractor output (CAVIAR_Distances-Extractor.py:147-151,196-198: one frame
+ * column, then one distance column per pair).  Formats rows x cols float32 values as
+ *     "<first_index + r*index_step>,<v>,<v>,...\n"      with `decimals` fixed decimals (printf "%.Nf" rounding)
+ * into `out` (capacity `cap` bytes) using the host cores.  Returns the number of bytes written, or a negative
+ * CV_E_* code (CV_E_NOMEM when `cap` is too small: 24 + 28*cols bytes per row always suffice). */
+int64_t caviar_format_csv(const float* values, int64_t rows, int64_t cols, int64_t row_stride_floats,
+                          int64_t first_index, int64_t index_step, int32_t decimals, char* out, int64_t cap);
+
 const char* caviar_last_error(void);
 int caviar_abi_version(void);
 

@@ -1,0 +1,118 @@
+"""Host logic of the Extractor drop-in: label grammar pinned to the reference's own outputs, topology / trajectory
+readers, atom selection, CSV formatting.  No GPU needed."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def ext():
+    import __graft_entry__ as g
+    g.build()
+    from caviar_b200 import extractor
+    return extractor
+
+
+@pytest.fixture(scope="module")
+def meta(golden_dir):
+    with open(os.path.join(golden_dir, "reference_cases.json")) as fh:
+        return json.load(fh)
+
+
+def test_label_grammar_matches_reference_vectors(ext, meta, tmp_path):
+    par = meta["parser"]                                   # produced by the reference's _parse_pair_token etc.
+    for tok, want in par["tokens"]:
+        got = ext.PairGrammar.token(tok)
+        assert ([list(got)] if got else []) == want, tok
+    for s, want in par["strings"]:
+        assert [list(p) for p in ext.PairGrammar.many(s.split(","))] == want, s
+    for case in par["files"]:
+        f = tmp_path / "pairs.txt"
+        f.write_text(case["body"])
+        assert [list(p) for p in ext.read_pairs(case["pairs"], str(f))] == case["result"]
+    with pytest.raises(SystemExit) as e:
+        ext.read_pairs("nothing here", "")
+    assert "Nessuna coppia valida" in str(e.value)
+
+
+def _toy_topology(n_res=12):
+    names, labels, first = [], [], []
+    res3 = ["ASP", "GLU", "ALA", "GLY", "SER", "THR", "LYS", "ARG", "HIS", "PRO", "VAL", "LEU"]
+    for r in range(n_res):
+        first.append(len(names))
+        labels.append(res3[r % len(res3)])
+        names += ["N", "H", "CA", "HA", "C", "O"] if r % 3 else ["N", "CA", "C", "O", "CB"]
+    return names, labels, first
+
+
+def test_prmtop_roundtrip_and_selection(ext, tmp_path):
+    from caviar_b200 import trajio
+    names, labels, first = _toy_topology()
+    path = str(tmp_path / "toy.prmtop")
+    trajio.write_prmtop(path, names, labels, first)
+    top = trajio.read_topology(path)
+    assert top.n_atoms == len(names) and top.n_res == len(labels)
+    assert top.atom_names == names and top.res_labels == labels and top.res_first_atom == first
+    ca = [top.atom_of(r) for r in range(top.n_res)]
+    assert all(names[a] == "CA" for a in ca) and ca[0] == 1 and ca[1] == first[1] + 2
+    labs = [("ASP", 22, "GLU", 23), ("ALA", 24, "LEU", 33)]
+    atoms = ext.select_atoms(top, labs, "sequential", 21)          # label - offset = 1-based residue index
+    assert atoms.tolist() == [[ca[0], ca[1]], [ca[2], ca[11]]]
+    with pytest.raises(SystemExit) as e:
+        ext.select_atoms(top, [("ASP", 21, "GLU", 23)], "sequential", 21)
+    assert "label-offset < 1" in str(e.value)
+    with pytest.raises(SystemExit):
+        ext.select_atoms(top, [("ASP", 22, "GLU", 99)], "sequential", 21)
+
+
+def test_pdb_resseq_selection(ext, tmp_path):
+    from caviar_b200 import trajio
+    lines = []
+    serial = 1
+    for resseq, res in ((40, "ASP"), (41, "GLU"), (45, "ALA")):
+        for nm in ("N", "CA", "C"):
+            lines.append(f"ATOM  {serial:5d} {nm:^4s} {res} A{resseq:4d}    {1.0:8.3f}{2.0:8.3f}{3.0:8.3f}  1.00  0.00")
+            serial += 1
+    p = tmp_path / "toy.pdb"
+    p.write_text("\n".join(lines) + "\nEND\n")
+    top = trajio.read_topology(str(p))
+    assert top.res_seq == [40, 41, 45] and top.n_atoms == 9
+    atoms = ext.select_atoms(top, [("ASP", 40, "ALA", 45)], "resSeq", 0)
+    assert atoms.tolist() == [[1, 7]]
+
+
+def test_netcdf_roundtrip_and_cell(tmp_path):
+    from caviar_b200 import trajio
+    from oracle import caviar_oracle as orc
+    rng = np.random.default_rng(0)
+    xyz = rng.uniform(0, 50, size=(7, 11, 3)).astype(np.float32)
+    p = str(tmp_path / "t.nc")
+    trajio.write_netcdf(p, xyz, [50.0, 51.0, 52.0], [109.4712206] * 3)
+    tr = trajio.Trajectory(p)
+    assert (tr.n_frames, tr.n_atoms) == (7, 11) and tr.box_kind() == "triclinic"
+    assert np.array_equal(tr.coords(0, 7), xyz) and np.array_equal(tr.coords(1, 7, 2), xyz[1:7:2])
+    cell = tr.cell(0, 7)
+    want = orc.box_matrix([50.0, 51.0, 52.0], [109.4712206] * 3)
+    assert np.allclose(cell[3], want, atol=1e-4) and cell[0, 0, 1] == 0 and cell[0, 0, 2] == 0 and cell[0, 1, 2] == 0
+    tr.close()
+    trajio.write_netcdf(p, xyz, [50.0, 51.0, 52.0])
+    tr = trajio.Trajectory(p)
+    assert tr.box_kind() == "ortho" and np.allclose(tr.cell(0, 2), [[50, 51, 52]] * 2)
+    tr.close()
+    trajio.write_netcdf(p, xyz)
+    tr = trajio.Trajectory(p)
+    assert tr.box_kind() is None and tr.cell(0, 2) is None
+    tr.close()
+
+
+def test_csv_rows_match_printf(ext):
+    rng = np.random.default_rng(1)
+    v = rng.uniform(0, 300, size=(257, 33)).astype(np.float32)
+    v[0, :6] = [0.00005, 0.12345, 0.12355, 7.99995, 0.0, 123456.7]
+    got = ext.format_rows(v, 1, 1, 4).decode()
+    want = "".join(f"{r + 1}," + ",".join("%.4f" % float(x) for x in v[r]) + "\n" for r in range(v.shape[0]))
+    assert got == want
+    assert ext.format_rows(v[:2, :2], 5, 3, 2).decode() == "".join(
+        f"{5 + 3 * r}," + ",".join("%.2f" % float(x) for x in v[r, :2]) + "\n" for r in range(2))

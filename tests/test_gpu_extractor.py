@@ -1,0 +1,98 @@
+"""End-to-end run of the Extractor drop-in on a synthetic Amber NetCDF + prmtop, checked against the CPU oracle."""
+import csv
+import json
+
+import numpy as np
+import pytest
+
+from oracle import caviar_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _system(tmp_path, box):
+    from caviar_b200 import trajio
+    rng = np.random.default_rng(9)
+    n_res, T = 60, 53
+    names, labels, first = [], [], []
+    res3 = ["ASP", "GLU", "ALA", "GLY", "SER", "THR", "LYS", "ARG", "HIS", "PRO"]
+    for r in range(n_res):
+        first.append(len(names))
+        labels.append(res3[r % 10])
+        names += ["N", "H", "CA", "HA", "C", "O", "CB"]
+    n_atoms = len(names)
+    L = np.array([38.0, 40.0, 36.0])
+    base = np.cumsum(rng.normal(0, 1.5, size=(n_atoms, 3)), axis=0) % L
+    xyz = ((base[None] + rng.normal(0, 0.4, size=(T, n_atoms, 3))) % L).astype(np.float32)
+    top = str(tmp_path / "sys.prmtop")
+    trajio.write_prmtop(top, names, labels, first)
+    nc = str(tmp_path / "traj.nc")
+    if box == "ortho":
+        trajio.write_netcdf(nc, xyz, L)
+    elif box == "triclinic":
+        trajio.write_netcdf(nc, xyz, L, [109.4712206] * 3)
+    else:
+        trajio.write_netcdf(nc, xyz)
+    ca = np.array([f + 2 for f in first])
+    return top, nc, xyz, L, ca, labels
+
+
+@pytest.mark.parametrize("box,stride", [("ortho", 1), ("triclinic", 2), (None, 3)])
+def test_extractor_cli_against_oracle(tmp_path, capsys, box, stride):
+    from caviar_b200 import extractor, trajio
+    top, nc, xyz, L, ca, labels = _system(tmp_path, box)
+    offset = 21
+    # the ranked-loading CSV CAVIAR-1.0.py writes (save_tic_csv, :141-147) is a valid --pairs-file
+    sel = [(0, 9), (3, 40), (59, 12), (7, 8), (3, 40)]
+    res_label = {i: f"{labels[i]}{i + 1 + offset}" for i in range(len(labels))}
+    rows = orc.tic_csv_rows([(a, b) for a, b in sel[:4]], np.array([0.5, -0.4, 0.3, 0.2]), res_label)
+    pf = tmp_path / "pooled_distances_TIC1.csv"
+    pf.write_text("\n".join(rows) + "\n")
+    out = tmp_path / "out.csv"
+    npy = tmp_path / "out.npy"
+    summ = tmp_path / "summary.json"
+    rc = extractor.main(["--top", top, "--traj", nc, "--pairs-file", str(pf), "--pairs", f"{res_label[3]}-{res_label[40]}",
+                         "--offset", str(offset), "--stride", str(stride), "--out", str(out),
+                         "--npy-out", str(npy), "--summary-out", str(summ)])
+    assert rc == 0
+    printed = capsys.readouterr().out
+    assert f"[DONE] Salvato CSV: {out}" in printed and "[INFO] Colonne:" in printed
+    # expected column order: --pairs first, then the file rows, de-duplicated (Extractor:69-86)
+    order = [(3, 40), (0, 9), (59, 12), (7, 8)]
+    want_cols = [f"{res_label[a]}-{res_label[b]}" for a, b in order]
+    with open(out) as fh:
+        table = list(csv.reader(fh))
+    assert table[0] == ["#Frame"] + want_cols
+    frames = xyz[::stride]
+    assert [int(r[0]) for r in table[1:]] == list(range(1, len(frames) + 1))
+    got = np.array([[float(v) for v in r[1:]] for r in table[1:]])
+    pairs = [(int(ca[a]), int(ca[b])) for a, b in order]
+    if box == "ortho":
+        cell = np.broadcast_to(L, (len(frames), 3))
+    elif box == "triclinic":
+        cell = trajio.cell_to_matrix(np.broadcast_to(L, (len(frames), 3)), np.full((len(frames), 3), 109.4712206))
+        cell = cell.astype(np.float32).astype(np.float64)
+    else:
+        cell = None
+    want = orc.pbc_pair_distances(frames, pairs, cell)
+    assert np.abs(got - want).max() <= 1e-4 + 0.5e-4            # 1e-4 A tolerance + 4-decimal rounding
+    d = np.load(npy)
+    assert d.shape == want.shape and np.abs(d - want).max() <= 1e-4
+    if box is None:                                             # no box: bit-exact reference arithmetic
+        assert d.tobytes() == orc.pair_distances(frames, pairs, n_jobs=1).tobytes()
+    s = json.load(open(summ))
+    assert s["frames"] == len(frames) and s["columns"] == want_cols
+    assert s["occupancy"] == (d.astype(np.float64) < 8.0).sum(0).tolist()
+    np.testing.assert_allclose(s["mean"], d.astype(np.float64).mean(0), rtol=1e-12)
+    assert s["frame_score"] == (d.astype(np.float64) < 8.0).sum(1).tolist()
+
+
+def test_extractor_error_paths(tmp_path):
+    from caviar_b200 import extractor
+    top, nc, xyz, L, ca, labels = _system(tmp_path, None)
+    with pytest.raises(SystemExit) as e:
+        extractor.main(["--top", top, "--traj", nc, "--pairs", "bogus"])
+    assert "Nessuna coppia valida" in str(e.value)
+    with pytest.raises(SystemExit) as e:
+        extractor.main(["--top", top, "--traj", nc, "--pairs", "ASP5-GLU30", "--offset", "21"])
+    assert "label-offset < 1" in str(e.value)
