@@ -280,7 +280,7 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
     // frame chunks of the work queue: about kItemsPerCta items per CTA, whole pipeline stages each
     {
         const int64_t fb = hp.frames_per_stage;
-        int64_t cf = (n_frames + hp.max_chunks - 1) / hp.max_chunks;
+        int64_t cf = std::max<int64_t>((n_frames + hp.max_chunks - 1) / hp.max_chunks, kMinChunkFrames);
         cf = std::max<int64_t>(fb, (cf + fb - 1) / fb * fb);
         if (cf > (1ll << 30)) return fail(CV_E_INVALID, "too many frames for one run: split the call");
         rp.chunk_frames = (int32_t)cf;
@@ -310,8 +310,8 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
     if (e != cudaSuccess) return fail(CV_E_CUDA, std::string("features_kernel launch: ") + cudaGetErrorString(e));
     g_launches += 1;
     if (want_agg) {
-        const unsigned blocks = (unsigned)((F + 255) / 256);
-        finalize_kernel<<<blocks, 256, 0, st>>>(rp.occ_part, rp.sum_part, rp.sq_part, F, rp.n_chunks,
+        const unsigned blocks = (unsigned)((F + 31) / 32);
+        finalize_kernel<<<blocks, dim3(32, kFinalizeSlices), 0, st>>>(rp.occ_part, rp.sum_part, rp.sq_part, F, rp.n_chunks,
                                                 reinterpret_cast<unsigned long long*>(agg->occupancy), agg->sum, agg->sumsq);
         CV_CUDA(cudaGetLastError());
         g_launches += 1;
@@ -434,7 +434,8 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
             launches += g_launches;
             coords = s.staged.as<float>();
         }
-        CvFrameOutputs fo{s.dist.as<float>(), s.angle.as<float>(), s.flags.as<uint32_t>(), s.score.as<int32_t>()};
+        CvFrameOutputs fo{out->dist ? s.dist.as<float>() : nullptr, out->angle ? s.angle.as<float>() : nullptr,
+                          out->flags ? s.flags.as<uint32_t>() : nullptr, out->score ? s.score.as<int32_t>() : nullptr};
         CvAggregates ag{occ.as<uint64_t>(), sum.as<double>(), sq.as<double>()};
         rc = caviar_run(plan, coords, frame_stride_floats, box_floats ? rec_all.as<float>() + t0 * kRecFloats : nullptr, n, &fo, want_agg ? &ag : nullptr, ws.p, s_run.s);
         if (rc != CV_OK) return rc;
