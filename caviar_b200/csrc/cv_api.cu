@@ -75,6 +75,22 @@ struct Event {
     cudaError_t create() { return e ? cudaSuccess : cudaEventCreateWithFlags(&e, cudaEventDisableTiming); }
     ~Event() { if (e) cudaEventDestroy(e); }
 };
+// memcpy between pageable user memory and the pinned bounce buffers, spread over a few host threads: one core
+// moves ~10 GB/s, PCIe 5 x16 wants ~55 GB/s.
+void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    const size_t kMin = 8u << 20;
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nt = std::min<size_t>(std::min<size_t>(hw ? hw : 4, 8), bytes / kMin);
+    if (nt <= 1) { memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> pool;
+    const size_t step = (bytes / nt + 4095) & ~(size_t)4095;
+    for (size_t k = 1; k < nt; ++k) {
+        const size_t lo = k * step, hi = std::min(bytes, lo + step);
+        if (lo < hi) pool.emplace_back([=] { memcpy((char*)dst + lo, (const char*)src + lo, hi - lo); });
+    }
+    memcpy(dst, src, std::min(bytes, step));
+    for (auto& t : pool) t.join();
+}
 bool is_pinned(const void* p) {
     if (!p) return true;
     cudaPointerAttributes a{};
@@ -402,8 +418,8 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
         if (!pd.live) return CV_OK;
         CV_CUDA(cudaEventSynchronize(set[k].downloaded.e));
         if (!out_pinned) {
-            if (out->dist) memcpy(out->dist + pd.t0 * P, set[k].h_dist.p, (size_t)pd.n * P * 4);
-            if (out->angle) memcpy(out->angle + pd.t0 * A, set[k].h_angle.p, (size_t)pd.n * A * 4);
+            if (out->dist) parallel_memcpy(out->dist + pd.t0 * P, set[k].h_dist.p, (size_t)pd.n * P * 4);
+            if (out->angle) parallel_memcpy(out->angle + pd.t0 * A, set[k].h_angle.p, (size_t)pd.n * A * 4);
             if (out->flags) memcpy(out->flags + pd.t0 * W, set[k].h_flags.p, (size_t)pd.n * W * 4);
             if (out->score) memcpy(out->score + pd.t0, set[k].h_score.p, (size_t)pd.n * 4);
         }
@@ -420,7 +436,7 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
         // upload
         const float* src = xyz_host + t0 * frame_stride_floats;
         if (!in_pinned) {
-            memcpy(s.h_in.p, src, (size_t)n * frame_stride_floats * 4);
+            parallel_memcpy(s.h_in.p, src, (size_t)n * frame_stride_floats * 4);
             src = s.h_in.as<float>();
         }
         CV_CUDA(cudaMemcpyAsync(s.xyz.p, src, (size_t)n * frame_stride_floats * 4, cudaMemcpyHostToDevice, s_up.s));
