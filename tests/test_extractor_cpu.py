@@ -116,3 +116,20 @@ def test_csv_rows_match_printf(ext):
     assert got == want
     assert ext.format_rows(v[:2, :2], 5, 3, 2).decode() == "".join(
         f"{5 + 3 * r}," + ",".join("%.2f" % float(x) for x in v[r, :2]) + "\n" for r in range(2))
+
+
+def test_residue_components_match_reference_vectors(meta, golden_dir):
+    """f4: thresholded mean-distance graph -> components, pinned to build_residue_components' own output."""
+    from caviar_b200.components import pair_means_from_aggregates, residue_components
+    gold = np.load(os.path.join(golden_dir, "distances.npz"))
+    agg = meta["aggregates"]
+    n, m = agg["n_res"], agg["minsep"]
+    pairs = [(i, j) for i in range(n) for j in range(i + m, n)]
+    d = gold["B_d"]                                                     # the reference's own (T, P) distances
+    means = pair_means_from_aggregates(d.astype(np.float64).sum(0), d.shape[0])
+    for cut_repr, want in agg["components"].items():
+        cut = float(cut_repr)
+        # the reference thresholds ITS float32-accumulated mean; skip cut-offs that sit within float32 rounding of one
+        if np.any(np.abs(means.astype(np.float64) - cut) < 4e-6 * cut):
+            continue
+        assert residue_components(n, pairs, means, cut) == want
