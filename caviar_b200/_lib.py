@@ -88,9 +88,16 @@ def _load():
     global LIB_PATH
     LIB_PATH = os.environ.get("CAVIAR_B200_LIB", LIB_PATH)      # A/B testing of alternative builds
     if not os.path.exists(LIB_PATH):
-        raise ImportError(
-            f"{LIB_PATH} is missing. caviar_b200 has no CPU or PyTorch fallback: build the sm_100a library first "
-            "(python -c 'import __graft_entry__ as g; g.build()'  or  python caviar_b200/build.py).")
+        # The library is a build artefact (git-ignored).  If it is missing but nvcc is at hand, compile the SAME
+        # sm_100a sources in-tree once; there is still no CPU or PyTorch code path -- without the library, no import.
+        try:
+            from . import build as _build
+            _build.build()
+        except Exception as exc:
+            raise ImportError(
+                f"{LIB_PATH} is missing and could not be built ({exc}). caviar_b200 has no CPU or PyTorch fallback: "
+                "build the sm_100a library first (python -c 'import __graft_entry__ as g; g.build()'  or  "
+                "python caviar_b200/build.py).") from exc
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)          # AttributeError here = header and library out of sync

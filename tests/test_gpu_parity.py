@@ -322,3 +322,57 @@ def test_size_independent_properties_at_scale(cb):
     assert (out.dist - out_b.dist).abs().max() <= DIST_TOL
     d64 = out.dist.double()
     np.testing.assert_allclose(agg.sum[:P].cpu().numpy(), d64.sum(0).cpu().numpy(), rtol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# 4. cell shapes: the image search must find the TRUE minimum image, not just agree with a 27-image oracle
+# ---------------------------------------------------------------------------------------------------------
+CELLS = {
+    "cubic_as_triclinic": ((40.0, 40.0, 40.0), (90.0, 90.0, 90.0)),
+    "hexagonal": ((35.0, 35.0, 50.0), (90.0, 90.0, 120.0)),
+    "rhombic_dodecahedron": ((45.0, 45.0, 45.0), (60.0, 60.0, 90.0)),
+    "truncated_octahedron": ((60.0, 60.0, 60.0), (109.4712206, 109.4712206, 109.4712206)),
+    "monoclinic": ((30.0, 44.0, 38.0), (90.0, 112.0, 90.0)),
+    "general": ((33.0, 41.0, 37.0), (75.0, 85.0, 70.0)),
+    "rhombohedral_60": ((40.0, 40.0, 40.0), (60.0, 60.0, 60.0)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CELLS))
+def test_true_minimum_image_for_cell_shapes(cb, name):
+    lengths, angles = CELLS[name]
+    h = orc.box_matrix(lengths, angles)
+    h32 = h.astype(np.float32)
+    h = h32.astype(np.float64)                           # the cell the device sees
+    rng = np.random.default_rng(abs(hash(name)) % 1000)
+    n, T = 300, 6
+    x = ((rng.random((T, n, 3)) * 3.0 - 1.0) @ h).astype(np.float32)     # atoms spread over several cells
+    pairs = rng.integers(0, n, size=(1200, 2))
+    triplets = rng.integers(0, n, size=(300, 3))
+    box = np.broadcast_to(h32, (T, 3, 3))
+    with cb.FeaturePlan(n, pairs, triplets, box="triclinic", pair_cutoff=12.0, hbond_dist_cutoff=15.0,
+                        hbond_angle_cutoff=90.0) as plan:
+        res = plan.features_host(x, box)
+    # brute force over 7x7x7 images in fp64
+    rngs = np.arange(-3, 4)
+    shifts = np.array([(a, b, c) for a in rngs for b in rngs for c in rngs], dtype=np.float64) @ h
+    x64 = x.astype(np.float64)
+    delta = x64[:, pairs[:, 0], :] - x64[:, pairs[:, 1], :]
+    brute = np.linalg.norm(delta[:, :, None, :] + shifts[None, None], axis=3).min(axis=2)
+    assert np.abs(res["dist"] - brute).max() <= DIST_TOL
+    # angles: arms by brute-force minimum image, skipping arms that are (nearly) equidistant to two images
+    def arm(i, j):
+        d = x64[:, triplets[:, i], :] - x64[:, triplets[:, j], :]
+        cand = d[:, :, None, :] + shifts[None, None]
+        ln = np.linalg.norm(cand, axis=3)
+        order = np.argsort(ln, axis=2)[:, :, :2]
+        best = np.take_along_axis(cand, order[:, :, :1, None], axis=2)[:, :, 0, :]
+        gap = np.take_along_axis(ln, order, axis=2)
+        return best, (gap[:, :, 1] - gap[:, :, 0]) > 1e-3, gap[:, :, 0]
+    u, ok_u, lu = arm(0, 1)
+    v, ok_v, lv = arm(2, 1)
+    cosang = np.einsum("tkc,tkc->tk", u, v) / np.maximum(lu * lv, 1e-300)
+    want = np.degrees(np.arccos(np.clip(cosang, -1, 1)))
+    ok = ok_u & ok_v & (lu > 1e-6) & (lv > 1e-6)
+    assert ok.mean() > 0.95
+    assert np.abs(res["angle"] - want)[ok].max() <= ANGLE_TOL
