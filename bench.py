@@ -397,6 +397,26 @@ def main():
                          f"triplet angles (27-image PBC) {r['triplets_s']:.2f}s",
                "pairs_only_value": Tc * P / max(r["pairs_s"] + r["aggregate_s"], 1e-9), "spot_check": check}
 
+    # ---- the reference's own shape through its own operator (B1), pageable numpy in / numpy out ----
+    native = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import caviar_oracle as orc          # cpu_baseline leg: the checker / CPU arm, never the product
+        Tn, nres = 7000, 300                              # T=7000, 300 residues, minsep 5
+        rng = np.random.default_rng(0)
+        Xn = (np.cumsum(rng.normal(0, 0.38, size=(nres, 3)), axis=0)[None]
+              + rng.normal(0, 0.05, size=(Tn, nres, 3))).astype(np.float32)
+        pl = [(i, j) for i in range(nres) for j in range(i + 5, nres)]
+        cb.compute_distances_parallel(Xn[:64], pl)        # warm-up
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter(); Dn = cb.compute_distances_parallel(Xn, pl); ts.append(time.perf_counter() - t0)
+        n_jobs = max((os.cpu_count() or 2) - 1, 1)
+        t0 = time.perf_counter(); Dr = orc.pair_distances(Xn, pl, n_jobs=n_jobs); cpu_s = time.perf_counter() - t0
+        native = {"call": "compute_distances_parallel(X (7000,300,3), all pairs minsep 5 -> P=43660)  [CAVIAR-1.0.py:110-122]",
+                  "ours_s": min(ts), "ours_evals_per_s": Tn * len(pl) / min(ts), "cpu_s": cpu_s, "cpu_threads": n_jobs,
+                  "cpu_evals_per_s": Tn * len(pl) / cpu_s, "bit_exact": bool(Dn.tobytes() == Dr.tobytes())}
+        del Dn, Dr
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -405,7 +425,8 @@ def main():
                                           % (coords_bytes(T, S) / 1e9), setup_s=round(t_setup, 1),
                                           parallelism=f"frame-sharded x{world}, one NCCL all-reduce of aggregates per step"),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-                "gpu_launches": launches_per_step * args.steps, "raw_frame_input": direct}
+                "gpu_launches": launches_per_step * args.steps, "raw_frame_input": direct,
+                "reference_native_shape": native}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
