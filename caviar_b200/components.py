@@ -44,3 +44,16 @@ def residue_components(n_res: int, pairs: Sequence[Tuple[int, int]], pair_means,
         root = find(r)
         labels[r] = seen.setdefault(root, len(seen))
     return labels
+
+
+def cohens_d_from_aggregates(sum_a, sumsq_a, n_a: int, sum_b, sumsq_b, n_b: int) -> np.ndarray:
+    """Per-pair Cohen's d between two ensembles from the kernel's fp64 sums (CAVIAR-1.0.py:539-545, :559-561):
+    ``(mean_a - mean_b) / (pooled_sd + 1e-12)`` with ``var(ddof=1)`` -- no pass over the (T, P) matrices needed."""
+    sa, qa = np.asarray(sum_a, dtype=np.float64), np.asarray(sumsq_a, dtype=np.float64)
+    sb, qb = np.asarray(sum_b, dtype=np.float64), np.asarray(sumsq_b, dtype=np.float64)
+    ma, mb = sa / n_a, sb / n_b
+    va = (qa - n_a * ma * ma) / (n_a - 1) if n_a > 1 else np.zeros_like(ma)
+    vb = (qb - n_b * mb * mb) / (n_b - 1) if n_b > 1 else np.zeros_like(mb)
+    va, vb = np.maximum(va, 0.0), np.maximum(vb, 0.0)
+    pooled = np.sqrt(((n_a - 1) * va + (n_b - 1) * vb) / max(n_a + n_b - 2, 1))
+    return (ma - mb) / (pooled + 1e-12)

@@ -133,3 +133,15 @@ def test_residue_components_match_reference_vectors(meta, golden_dir):
         if np.any(np.abs(means.astype(np.float64) - cut) < 4e-6 * cut):
             continue
         assert residue_components(n, pairs, means, cut) == want
+
+
+def test_cohens_d_from_running_sums_matches_reference_formula():
+    from caviar_b200.components import cohens_d_from_aggregates
+    from oracle import caviar_oracle as orc
+    rng = np.random.default_rng(4)
+    a = rng.normal(7.0, 1.5, size=(400, 6)).astype(np.float32)
+    b = rng.normal(7.6, 0.9, size=(250, 6)).astype(np.float32)
+    a64, b64 = a.astype(np.float64), b.astype(np.float64)
+    got = cohens_d_from_aggregates(a64.sum(0), (a64 ** 2).sum(0), 400, b64.sum(0), (b64 ** 2).sum(0), 250)
+    want = np.array([orc.cohens_d(a[:, k], b[:, k]) for k in range(6)])
+    np.testing.assert_allclose(got, want, rtol=1e-9)
