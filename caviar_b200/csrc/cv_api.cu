@@ -262,6 +262,13 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
     if (n_frames < 0) return fail(CV_E_INVALID, "negative frame count");
     if (n_frames == 0) return CV_OK;
     const HostPlan& hp = plan->hp;
+    {
+        int cur = -1;
+        CV_CUDA(cudaGetDevice(&cur));
+        if (cur != plan->device)
+            return fail(CV_E_INVALID, "plan was created on device " + std::to_string(plan->device) +
+                                          " but the current device is " + std::to_string(cur));
+    }
     if (!coords_dev) return fail(CV_E_INVALID, "null coordinate pointer");
     if (hp.desc.box_kind != CV_BOX_NONE && !boxrec_dev) return fail(CV_E_INVALID, "plan has a box but boxrec is null");
     const bool want_agg = agg && (agg->occupancy || agg->sum || agg->sumsq);

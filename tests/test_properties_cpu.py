@@ -1,0 +1,90 @@
+"""Property tests (hypothesis) of the oracle's extension semantics and of the host-side planner."""
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from oracle import caviar_oracle as orc
+
+
+@st.composite
+def systems(draw):
+    n = draw(st.integers(4, 24))
+    t = draw(st.integers(1, 4))
+    seed = draw(st.integers(0, 2 ** 31 - 1))
+    rng = np.random.default_rng(seed)
+    lengths = rng.uniform(12.0, 30.0, size=3)
+    angles = rng.uniform(75.0, 105.0, size=3)        # always a valid (non-degenerate) cell
+    h = orc.box_matrix(lengths, angles)
+    x = rng.random((t, n, 3)) @ h
+    pairs = rng.integers(0, n, size=(draw(st.integers(1, 12)), 2))
+    trips = rng.integers(0, n, size=(draw(st.integers(1, 6)), 3))
+    return x, h, pairs, trips, rng
+
+
+@settings(max_examples=40, deadline=None)
+@given(systems())
+def test_oracle_pbc_invariances(sysm):
+    x, h1, pairs, trips, rng = sysm
+    h = np.broadcast_to(h1, (x.shape[0], 3, 3))          # explicit per-frame cells ((3,3) is ambiguous when T == 3)
+    d = orc.pbc_pair_distances(x, pairs, h)
+    # swapping (i, j) leaves the distance unchanged
+    assert np.allclose(orc.pbc_pair_distances(x, pairs[:, ::-1], h), d, atol=1e-9)
+    # translating any atom by a lattice vector leaves every minimum-image quantity unchanged
+    x2 = x.copy()
+    shift = rng.integers(-2, 3, size=(x.shape[1], 3)).astype(np.float64) @ h1
+    x2 += shift[None]
+    assert np.allclose(orc.pbc_pair_distances(x2, pairs, h), d, atol=1e-8)
+    # angles: skip arms that are (nearly) equidistant to two images -- there the angle is not well defined
+    ang1, ang2 = orc.triplet_angles(x, trips, h), orc.triplet_angles(x2, trips, h)
+    arm_u = orc.pbc_pair_distances(x, trips[:, [0, 1]], h)
+    arm_v = orc.pbc_pair_distances(x, trips[:, [2, 1]], h)
+    coef = np.array([(a, b, c) for a in range(-2, 3) for b in range(-2, 3) for c in range(-2, 3) if (a, b, c) != (0, 0, 0)])
+    half = 0.5 * np.linalg.norm(coef @ h1, axis=1).min()        # below this an arm has a unique minimum image
+    safe = (arm_u < 0.9 * half) & (arm_v < 0.9 * half) & (arm_u > 1e-6) & (arm_v > 1e-6)
+    assert np.allclose(ang1[safe], ang2[safe], atol=1e-6)
+    # never longer than the plain Euclidean distance; never longer than half the cell diagonal sum
+    assert (d <= orc.pbc_pair_distances(x, pairs, None) + 1e-9).all()
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(1, 60), st.integers(1, 70), st.integers(0, 2 ** 31 - 1), st.floats(2.0, 14.0))
+def test_flag_aggregates_are_consistent(t, p, seed, cut):
+    rng = np.random.default_rng(seed)
+    d = rng.uniform(1.0, 15.0, size=(t, p)).astype(np.float32)
+    f = orc.contact_flags(d, cut)
+    assert np.array_equal(f, d < orc.f32_at_or_above(cut))               # float32 threshold == double compare
+    words = orc.pack_flags(f)
+    assert np.array_equal(orc.unpack_flags(words, p), f)
+    assert int(orc.occupancy(f).sum()) == int(orc.frame_scores(f).sum())  # checksum of checksums
+
+
+@settings(max_examples=30, deadline=None)
+@given(st.integers(2, 3000), st.integers(0, 4000), st.integers(0, 900), st.integers(0, 2 ** 31 - 1),
+       st.sampled_from([None, "ortho", "triclinic"]), st.sampled_from([None, "direct", "staged"]))
+def test_planner_invariants(n_atoms, n_pairs, n_trip, seed, box, force):
+    import __graft_entry__ as g
+    g.build()
+    import caviar_b200 as cb
+    if n_pairs + n_trip == 0:
+        n_pairs = 1
+    rng = np.random.default_rng(seed)
+    pairs = rng.integers(0, n_atoms, size=(n_pairs, 2))
+    trips = rng.integers(0, n_atoms, size=(n_trip, 3))
+    info = cb.FeaturePlan(n_atoms, pairs, trips, box=box, force=force, describe_only_sms=148).info
+    used = np.unique(np.concatenate([pairs.ravel(), trips.ravel()]))
+    assert info["n_features"] == n_pairs + n_trip
+    assert info["n_distinct_atoms"] == len(used)
+    assert info["n_flag_words"] == (n_pairs + 31) // 32 + (n_trip + 31) // 32
+    assert info["n_tiles"] == -(-n_pairs // 896) + -(-n_trip // 896) or info["n_tiles"] >= 1
+    assert 1 <= info["n_ctas"] <= 296
+    assert info["workspace_bytes"] >= 256 + 24 * (n_pairs + n_trip)
+    if info["mode_name"] == "direct":
+        assert force == "direct" and info["smem_bytes"] == 0
+    else:
+        assert 2 <= info["stages"] <= 8 and info["frames_per_stage"] >= 1
+        assert info["smem_bytes"] <= 113 * 1024 or info["n_ctas"] <= 148
+    if info["mode_name"] == "staged":
+        s = info["staged_floats_per_frame"]
+        assert s % 12 == 0 and s >= 3 * len(used) and s <= 3 * (2 * n_pairs + 3 * n_trip) + 12 * info["n_tiles"]
+    if info["mode_name"] == "zerocopy":
+        assert force is None and n_atoms % 4 == 0 and n_atoms * 12 <= 48 * 1024
