@@ -512,6 +512,36 @@ extern "C" int caviar_pair_distances_host(const float* xyz_host, int64_t n_frame
     return rc;
 }
 
+extern "C" int caviar_pair_distances_host_f64(const double* xyz_host, int64_t n_frames, int32_t n_atoms,
+                                              const int32_t* pairs, int64_t n_pairs, double* dist_host) {
+    g_launches = 0;
+    if (n_frames < 0 || n_atoms <= 0 || n_pairs <= 0) return fail(CV_E_INVALID, "bad shape");
+    if (n_frames == 0) return CV_OK;
+    if (!xyz_host || !pairs || !dist_host) return fail(CV_E_INVALID, "null argument");
+    for (int64_t k = 0; k < 2 * n_pairs; ++k)
+        if (pairs[k] < 0 || pairs[k] >= n_atoms) return fail(CV_E_INVALID, "pair index out of range");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+        return fail(CV_E_NO_DEVICE, "no CUDA device: caviar_b200 has no CPU fallback");
+    DevBuf d_pairs, d_xyz, d_out;
+    CV_CUDA(d_pairs.alloc((size_t)n_pairs * 8));
+    CV_CUDA(cudaMemcpy(d_pairs.p, pairs, (size_t)n_pairs * 8, cudaMemcpyHostToDevice));
+    const int64_t row_in = 24ll * n_atoms, row_out = 8ll * n_pairs;
+    const int64_t TB = std::max<int64_t>(1, std::min<int64_t>(n_frames, (512ll << 20) / (row_in + row_out)));
+    CV_CUDA(d_xyz.alloc((size_t)TB * row_in));
+    CV_CUDA(d_out.alloc((size_t)TB * row_out));
+    for (int64_t t0 = 0; t0 < n_frames; t0 += TB) {
+        const int64_t n = std::min<int64_t>(TB, n_frames - t0);
+        CV_CUDA(cudaMemcpy(d_xyz.p, xyz_host + t0 * 3ll * n_atoms, (size_t)n * row_in, cudaMemcpyHostToDevice));
+        dim3 grid((unsigned)((n_pairs + 255) / 256), (unsigned)std::min<int64_t>(n, 4096));
+        pair_distances_f64_kernel<<<grid, 256>>>(d_xyz.as<double>(), n, n_atoms, d_pairs.as<int2>(), n_pairs, d_out.as<double>());
+        CV_CUDA(cudaGetLastError());
+        g_launches += 1;
+        CV_CUDA(cudaMemcpy(dist_host + t0 * n_pairs, d_out.p, (size_t)n * row_out, cudaMemcpyDeviceToHost));
+    }
+    return CV_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // CSV rows (host): fixed-point formatting without printf
 // ------------------------------------------------------------------------------------------------

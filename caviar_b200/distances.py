@@ -35,18 +35,23 @@ def compute_distances_parallel(X_xyz, pairs, n_jobs=None, chunk_size=8000):
     ``n_jobs`` and ``chunk_size`` are accepted for signature compatibility and ignored: the reference's
     joblib threads over 8000-pair chunks (CAVIAR-1.0.py:113,121) have no counterpart on the device.
     Reference behaviour kept: negative indices wrap, out-of-range raises IndexError, an empty pair list
-    raises ValueError (np.concatenate of nothing), float64 input gives float64 output (evaluated in
-    float32 on the device -- the callers cast to float32 anyway, CAVIAR-1.0.py:337).
+    raises ValueError (np.concatenate of nothing), float64 input gives float64 output (a float64 kernel
+    with the same operation order, bit-exact as well).
     """
     X = np.asarray(X_xyz)
     if X.ndim != 3 or X.shape[2] != 3:
         raise ValueError(f"X_xyz must be (T, n, 3), got {X.shape}")
     if len(pairs) == 0:
         raise ValueError("need at least one array to concatenate")
-    out_dtype = np.float64 if X.dtype == np.float64 else np.float32
     T, n = X.shape[0], X.shape[1]
     idx = _index_array(pairs, 2, n, "pairs")
+    if X.dtype == np.float64:
+        # numpy type propagation: float64 coordinates give float64 distances (the callers cast afterwards, :337)
+        Xc = np.ascontiguousarray(X)
+        D64 = np.empty((T, len(idx)), dtype=np.float64)
+        check(_lib.lib.caviar_pair_distances_host_f64(Xc.ctypes.data, T, n, idx.ctypes.data, len(idx), D64.ctypes.data))
+        return D64
     Xc = np.ascontiguousarray(X, dtype=np.float32)
     D = _result_array(T, len(idx))
     check(_lib.lib.caviar_pair_distances_host(Xc.ctypes.data, T, n, idx.ctypes.data, len(idx), D.ctypes.data))
-    return D if out_dtype == np.float32 else D.astype(np.float64)
+    return D

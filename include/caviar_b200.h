@@ -177,6 +177,11 @@ int caviar_pair_distances_host(const float* xyz_host, int64_t n_frames, int32_t 
 int64_t caviar_format_csv(const float* values, int64_t rows, int64_t cols, int64_t row_stride_floats,
                           int64_t first_index, int64_t index_step, int32_t decimals, char* out, int64_t cap);
 
+/* float64 flavour of compute_distances_parallel: the reference returns float64 when X is float64 (numpy type
+ * propagation at CAVIAR-1.0.py:118-119).  Same arithmetic order in IEEE double, bit-exact; HBM-bound gather kernel. */
+int caviar_pair_distances_host_f64(const double* xyz_host, int64_t n_frames, int32_t n_atoms,
+                                   const int32_t* pairs, int64_t n_pairs, double* dist_host);
+
 const char* caviar_last_error(void);
 int caviar_abi_version(void);
 

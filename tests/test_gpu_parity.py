@@ -49,7 +49,11 @@ def test_compute_distances_parallel_float64_input(cb, gold):
     pairs = [(int(a), int(b)) for a, b in gold["E_pairs"]]
     got = cb.compute_distances_parallel(gold["E_x"], pairs)
     assert got.dtype == np.float64                      # reference: float64 in, float64 out
-    np.testing.assert_allclose(got, gold["E_d"], rtol=3e-7)   # evaluated in float32 on the device
+    assert _bits(got) == _bits(gold["E_d"])             # float64 kernel, same operation order: bit-exact
+    rng = np.random.default_rng(12)
+    x = rng.normal(0, 30, size=(9, 41, 3))
+    pr = [(int(a), int(b)) for a, b in rng.integers(-41, 41, size=(500, 2))]
+    assert _bits(cb.compute_distances_parallel(x, pr)) == _bits(orc.pair_distances(x, pr, n_jobs=1))
 
 
 def test_compute_distances_parallel_errors(cb, gold):
