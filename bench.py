@@ -52,7 +52,7 @@ def parse_args():
 # clocks
 # ---------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi sampled every 100 ms while the timed region runs."""
+    """nvidia-smi sampled every 20 ms while the warm-up and timed steps run."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -65,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -97,8 +97,18 @@ class ClockSampler:
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        # "under load" = the samples at the highest power draw half (idle samples before the first kernel are dropped)
+        pw = []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            try:
+                pw.append(float(f[3]))
+            except (ValueError, IndexError):
+                pw.append(0.0)
+        loaded = [c for c, w in zip(sm, pw) if pw and w >= 0.5 * max(pw)] or sm
+        return {"sm_mhz": float(np.median(loaded)) if loaded else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "samples_under_load": len(loaded), "power_w_max": max(pw) if pw else None,
+                "reasons": sorted(reasons)}
 
 
 def measured_peak():
@@ -258,12 +268,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)           # samples through warm-up and the timed region (both are load)
+    sampler.start()
+    time.sleep(0.3)                              # let nvidia-smi come up before the kernels start
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
     launches_per_step = plan.last_launches
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
            torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
