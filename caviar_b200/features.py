@@ -158,7 +158,7 @@ class FeaturePlan:
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     def prepare_box(self, box):
-        """Raw per-frame boxes (torch CUDA float32 (T,3) | (T,9) | (T,3,3)) -> box records (T, 76)."""
+        """Raw per-frame boxes (torch CUDA float32 (T,3) | (T,9) | (T,3,3)) -> box records (T, boxrec_floats_per_frame)."""
         import torch
         if self.box_kind == BOX_NONE:
             return None

@@ -88,7 +88,7 @@ typedef struct CvPlanInfo {
     int32_t  stages;                  /* TMA pipeline depth (0 in direct mode) */
     int32_t  frames_per_stage;
     int32_t  smem_bytes;              /* dynamic shared memory per CTA */
-    int32_t  partial_slots;           /* frame partitions whose partial aggregates are reduced */
+    int32_t  partial_slots;           /* max frame chunks per run = rows of the partial-aggregate buffer */
     int64_t  n_features;              /* P + A */
     int64_t  n_flag_words;            /* ceil(P/32) + ceil(A/32) uint32 words per frame */
     int64_t  n_distinct_atoms;        /* U */
