@@ -190,23 +190,28 @@ inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
     } else {
         const int gb = max_grp_floats * 4;
         const int rec_b = d.box_kind != CV_BOX_NONE ? kRecFloats * 4 : 0;
-        int fb = std::max(1, std::min(16, (28 * 1024) / std::max(gb, 1)));
-        if (hp.whole_frame && (d.n_atoms % 4 != 0 || hp.mode == CV_MODE_STAGED)) { /* staged blocks are padded: any fb */ }
-        const int stage_total = fb * (gb + rec_b);
         const int bar_bytes = 2 * kMaxStages * 8 + kMaxStages * 24;   // mbarriers + per-stage work metadata
-        // resident CTAs per SM: 3 when two stages fit in a third of the shared memory (more warps hide the
-        // dependent-issue latency of the image search), else 2, else 1.  CAVIAR_OCC overrides (experiments).
+        const int frame_b = std::max(gb + rec_b, 1);
+        // Ring geometry.  Per-stage costs (barrier wait, metadata, release) are paid per warp, so few LARGE stages win:
+        // two stages of as many frames as fit beat four single-frame stages by 5 % on config 3.  2 CTAs/SM when two
+        // stages of >= 1 frame fit in half of the shared memory (110 KB), else 1 CTA/SM.  CAVIAR_OCC / CAVIAR_FB
+        // override for experiments.
         int want_occ = 2;
-        if (const char* e = std::getenv("CAVIAR_OCC")) want_occ = std::max(1, std::min(3, atoi(e)));
-        int ns = 0;
+        if (const char* e = std::getenv("CAVIAR_OCC")) want_occ = std::max(1, std::min(2, atoi(e)));
+        const int budget[3] = {0, 220 * 1024, 110 * 1024};
+        int fb = 0, ns = 0;
         hp.occupancy = 0;
-        const int budget[4] = {0, 220 * 1024, 110 * 1024, 73 * 1024};
-        const int min_stages[4] = {0, 2, 3, 2};
         for (int occ = want_occ; occ >= 1 && hp.occupancy == 0; --occ) {
-            const int n = (budget[occ] - bar_bytes) / stage_total;
-            if (n >= min_stages[occ]) { hp.occupancy = occ; ns = std::min(n, occ == 1 ? kMaxStages : 4); }
+            const int room = budget[occ] - bar_bytes;
+            int f = std::min(16, room / (2 * frame_b));
+            if (const char* e = std::getenv("CAVIAR_FB")) f = std::min(f, std::max(1, atoi(e)));
+            if (f >= 1) {
+                hp.occupancy = occ; fb = f;
+                ns = std::max(2, std::min(f == 1 ? 4 : 2, room / (f * frame_b)));
+            }
         }
         if (hp.occupancy == 0) return "a column tile's coordinate block does not fit in shared memory";
+        const int stage_total = fb * frame_b;
         hp.frames_per_stage = fb; hp.n_stages = ns; hp.stage_floats = fb * max_grp_floats;
         hp.smem_bytes = ns * stage_total + bar_bytes;
     }
