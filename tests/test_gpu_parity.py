@@ -380,3 +380,26 @@ def test_true_minimum_image_for_cell_shapes(cb, name):
     ok = ok_u & ok_v & (lu > 1e-6) & (lv > 1e-6)
     assert ok.mean() > 0.95
     assert np.abs(res["angle"] - want)[ok].max() <= ANGLE_TOL
+
+
+def test_aggregates_are_bit_reproducible_run_to_run(cb):
+    """The work queue hands items to CTAs in a timing-dependent order, but every item writes its own partial row
+    and finalize sums the rows in a fixed order: repeated runs must agree bit for bit (fp64 sums included)."""
+    import torch
+    from caviar_b200 import synthetic as syn
+    top = syn.make_topology(3, n_pairs=4000, n_triplets=900)
+    T = 3000
+    pairs, triplets = syn.compact_indices(top)
+    x = syn.device_frames(top, T)
+    box = torch.from_numpy(syn.boxes_for(top, T)).cuda()
+    with cb.FeaturePlan(x.shape[1], pairs, triplets, box="triclinic") as plan:
+        rec, staged = plan.prepare_box(box), plan.stage(x)
+        runs = []
+        for _ in range(3):
+            agg = plan.new_aggregates()
+            out = plan.run(staged, rec, aggregates=agg)
+            torch.cuda.synchronize()
+            runs.append((agg.occupancy.clone(), agg.sum.clone(), agg.sumsq.clone(), out.score.clone(), out.dist.clone()))
+    for r in runs[1:]:
+        for a, b in zip(runs[0], r):
+            assert torch.equal(a, b)
