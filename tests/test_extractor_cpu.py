@@ -145,3 +145,22 @@ def test_cohens_d_from_running_sums_matches_reference_formula():
     got = cohens_d_from_aggregates(a64.sum(0), (a64 ** 2).sum(0), 400, b64.sum(0), (b64 ** 2).sum(0), 250)
     want = np.array([orc.cohens_d(a[:, k], b[:, k]) for k in range(6)])
     np.testing.assert_allclose(got, want, rtol=1e-9)
+
+
+def test_all_pairs_and_trim_mirror_the_reference(meta):
+    from caviar_b200.selection import all_pairs, ca_atom_indices, trim_ca_indices
+    from oracle import caviar_oracle as orc
+    for n, m in ((48, 5), (10, 1), (7, 0), (6, 9), (1, 5), (300, 5)):
+        want = np.array(orc.all_pairs(n, m), dtype=np.int32).reshape(-1, 2)
+        assert np.array_equal(all_pairs(n, m), want), (n, m)
+    assert len(all_pairs(1000, 5)) == 495510
+    idx = list(range(100, 130))
+    for key, want in meta["aggregates"]["trim"].items():          # produced by the reference's _trim_ca_indices
+        tn, tc = (int(v) for v in key.split(","))
+        assert list(trim_ca_indices(idx, tn, tc)) == want
+    with pytest.raises(SystemExit):
+        trim_ca_indices(idx, 20, 10)
+
+    class _Top:
+        atom_names = ["N", "CA", "C", "O", "N", "H", "CA", "C"]
+    assert ca_atom_indices(_Top()).tolist() == [1, 6]
