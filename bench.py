@@ -222,10 +222,20 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL logs (its version banner included) go to stdout by default: send them to stderr so that rank 0's
-        # stdout carries exactly ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL writes its version banner to stdout (C level) when the communicator comes up; rank 0's stdout must
+        # carry exactly ONE JSON line, so file descriptor 1 points at stderr until the first collective is through.
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     top = syn.make_topology(args.config)
     cfg = top.cfg
