@@ -434,6 +434,13 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
         return CV_OK;
     };
 
+    // On any early error return, in-flight copies into the caller's buffers must have finished first.
+    struct Quiesce {
+        Stream &a, &b, &c;
+        bool armed = true;
+        ~Quiesce() { if (armed) { cudaStreamSynchronize(a.s); cudaStreamSynchronize(b.s); cudaStreamSynchronize(c.s); } }
+    } quiesce{s_up, s_run, s_down};
+
     for (int64_t b = 0; b < n_blocks; ++b) {
         const int k = (int)(b & 1);
         Set& s = set[k];
@@ -488,6 +495,7 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
         CV_CUDA(cudaMemcpy(out->sumsq, sq.p, (size_t)F * 8, cudaMemcpyDeviceToHost));
     }
     CV_CUDA(cudaStreamSynchronize(s_run.s));
+    quiesce.armed = false;
     g_launches = launches;
     return CV_OK;
 }
