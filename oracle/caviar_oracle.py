@@ -263,6 +263,8 @@ def _as_box_matrices(box, n_frames: int):
     b = np.asarray(box, dtype=np.float64)
     if b.shape == (3,):
         b = np.broadcast_to(b, (n_frames, 3))
+    if b.shape == (3, 3) and n_frames == 3 and b[0, 1] == 0 and b[0, 2] == 0 and b[1, 2] == 0:
+        b = np.broadcast_to(b, (3, 3, 3))      # T == 3: a lower-triangular (3,3) is a cell, not three length rows
     if b.shape == (n_frames, 3):
         h = np.zeros((n_frames, 3, 3))
         h[:, 0, 0], h[:, 1, 1], h[:, 2, 2] = b[:, 0], b[:, 1], b[:, 2]
