@@ -308,6 +308,21 @@ def main():
     evals_per_step = world * T * (P + A)
     value = evals_per_step / (ms_per_step * 1e-3)
 
+    # ---- size-independent property at the full size: checksum of checksums (sum of frame scores == sum of
+    #      occupancies == number of set flag bits), on the outputs of the last timed step ----
+    score_sum = out.score.sum(dtype=torch.int64)
+    bits = out.flags.view(torch.uint8)
+    lut = torch.tensor([bin(i).count("1") for i in range(256)], dtype=torch.int64, device=dev)
+    bit_sum = torch.zeros((), dtype=torch.int64, device=dev)
+    for c0 in range(0, bits.shape[0], 8192):
+        bit_sum += lut[bits[c0:c0 + 8192].long()].sum()
+    sums = torch.stack([score_sum, bit_sum])
+    if world > 1:
+        dist.all_reduce(sums)                       # scores / flags are rank-local, the occupancy is already global
+    occ_sum = int(agg.occupancy.sum())
+    full_check = {"score_sum": int(sums[0]), "flag_bits": int(sums[1]), "occupancy_sum": occ_sum,
+                  "equal": bool(int(sums[0]) == int(sums[1]) == occ_sum)}
+
     # ---- roofline of the fused kernel (algorithmic bytes per launch / its average duration) ----
     peak, peak_src = measured_peak()
     alg_bytes = int(info["algorithmic_bytes_per_frame"]) * T
@@ -448,7 +463,7 @@ def main():
                                           parallelism=f"frame-sharded x{world}, one NCCL all-reduce of aggregates per step"),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
                 "gpu_launches": launches_per_step * args.steps, "raw_frame_input": direct,
-                "reference_native_shape": native}
+                "reference_native_shape": native, "full_size_check": full_check}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -35,4 +35,5 @@ def test_bench_line_contract():
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["spot_check"]["max_angle_err_deg"] <= 1e-3
     assert d["value"] > 100 * c["value"]
     assert d["reference_native_shape"]["bit_exact"] is True
+    assert d["full_size_check"]["equal"] is True and d["full_size_check"]["score_sum"] > 0
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
