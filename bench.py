@@ -63,9 +63,11 @@ class ClockSampler:
         self.lines = []
 
     def start(self):
+        if os.environ.get("CAVIAR_SMI_MS") == "0":
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", os.environ.get("CAVIAR_SMI_MS", "20"), "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()

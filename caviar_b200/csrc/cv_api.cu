@@ -300,14 +300,25 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
     if (out) { rp.dist = out->dist; rp.angle = out->angle; rp.flags = out->flags; rp.score = out->score; }
     rp.P = hp.P; rp.A = hp.A; rp.W = hp.W; rp.Wp = hp.Wp;
     const long long F = hp.P + hp.A;
-    // frame chunks of the work queue: about kItemsPerCta items per CTA, whole pipeline stages each
+    // Frame chunks of the work queue: about kItemsPerCta items per CTA, whole pipeline stages each.  The last
+    // quarter of the frames is cut into chunks a quarter the size, so that the CTAs run dry within a quarter item
+    // of each other (the queue is chunk-major: small chunks are handed out last).
     {
         const int64_t fb = hp.frames_per_stage;
-        int64_t cf = std::max<int64_t>((n_frames + hp.max_chunks - 1) / hp.max_chunks, kMinChunkFrames);
-        cf = std::max<int64_t>(fb, (cf + fb - 1) / fb * fb);
+        const int64_t unit = 4 * fb;
+        int64_t cf = std::max<int64_t>((7 * n_frames / 4 + hp.max_chunks - 1) / hp.max_chunks, kMinChunkFrames);
+        cf = std::max<int64_t>(unit, (cf + unit - 1) / unit * unit);
         if (cf > (1ll << 30)) return fail(CV_E_INVALID, "too many frames for one run: split the call");
+        const int64_t tf = cf / 4;
+        int64_t n_big = (3 * n_frames / 4) / cf;
+        int64_t n_small = (n_frames - n_big * cf + tf - 1) / tf;
+        if (tf < kMinChunkFrames || n_big + n_small > hp.max_chunks) {      // short run: uniform chunks
+            n_big = (n_frames + cf - 1) / cf; n_small = 0;
+        }
         rp.chunk_frames = (int32_t)cf;
-        rp.n_chunks = (int32_t)((n_frames + cf - 1) / cf);
+        rp.tail_frames = (int32_t)tf;
+        rp.n_big_chunks = (int32_t)n_big;
+        rp.n_chunks = (int32_t)(n_big + n_small);
     }
     rp.queue = reinterpret_cast<unsigned int*>(workspace_dev);
     if (want_agg) {

@@ -49,6 +49,8 @@ struct RunParams {
     int32_t n_stages;
     int32_t stage_floats;       // floats reserved per pipeline stage for coordinates
     int32_t chunk_frames;       // frames per work item (multiple of frames_per_stage)
+    int32_t tail_frames;        // frames per item of the last chunks (chunk_frames / 4): guided scheduling, small tail
+    int32_t n_big_chunks;       // chunks [0, n_big_chunks) have chunk_frames frames, the rest tail_frames
     int32_t n_chunks;           // work items = n_chunks * n_tiles, chunk-major
     unsigned int* queue;        // work counter, zeroed before the launch
     float*    dist;
