@@ -70,6 +70,6 @@ struct RunParams {
 constexpr int kQueueBytes = 256;        // the work counter lives at the head of the caller's workspace
 constexpr int kMinChunkFrames = 32;     // ... but never fewer frames per item than this (short blocks of the host path)
 constexpr int kFinalizeSlices = 8;      // chunk slices summed in parallel, then combined in a fixed order
-constexpr int kItemsPerCta = 16;        // work items per CTA the chunking aims for (tail imbalance <= ~1/16)
+constexpr int kItemsPerCta = 32;        // work items per CTA the chunking aims for (tail imbalance <= ~1/16)
 
 }  // namespace cv
