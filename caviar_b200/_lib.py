@@ -42,6 +42,7 @@ class CvPlanInfo(C.Structure):
         ("n_features", C.c_int64), ("n_flag_words", C.c_int64), ("n_distinct_atoms", C.c_int64),
         ("staged_floats_per_frame", C.c_int64), ("boxrec_floats_per_frame", C.c_int64),
         ("workspace_bytes", C.c_int64), ("algorithmic_bytes_per_frame", C.c_int64),
+        ("gather_bank_conflicts", C.c_int64),
     ]
 
     def as_dict(self):

@@ -30,6 +30,7 @@ struct HostPlan {
     std::vector<int32_t> src_off;      // staged float j of a frame <- float src_off[j] of the input frame
     int64_t staged_floats = 0;
     int64_t n_distinct = 0;
+    int64_t bank_conflict_refs = 0;    // gather references left on an already-used shared-memory bank (staged mode)
     int frames_per_stage = 1, n_stages = 0, stage_floats = 0, smem_bytes = 0, whole_frame = 0;
     int max_chunks = 1;                // upper bound of frame chunks per run (sizes the workspace)
     int64_t P = 0, A = 0, W = 0, Wp = 0;
@@ -57,6 +58,70 @@ inline void split_tiles(int64_t n, int& n_tiles, int& width) {
     int64_t w = (n + c - 1) / c;
     width = round_up((int)w, 32);
     n_tiles = (int)((n + width - 1) / width);
+}
+
+// Where does each distinct atom of a tile sit inside the tile's staged block?  The consumers gather with LDS from
+// 3*slot (+0,+1,+2): the 32 lanes of one gather instruction read the atoms of 32 consecutive tile-local features in
+// one role, and two lanes collide on a shared-memory bank exactly when their slots are congruent mod 32 (3 is
+// invertible mod 32).  The block order is ours to choose, so atoms get a "colour" = slot mod 32 such that the atoms
+// of one gather have distinct colours wherever possible (greedy, least-used colour first to keep the classes
+// balanced); slot = 32*row + colour with each class sorted by atom index.  A block sorted by atom index (the first
+// version) measured 55 % of all shared-memory wavefronts as bank-conflict replays.
+// Returns the number of references that still collide (atoms shared between gathers that had been coloured before).
+inline int64_t assign_bank_slots(const HostPlan& hp, const TileDesc& t, const std::vector<int32_t>& ua,
+                                 std::vector<int32_t>& slot_of, int& n_slots) {
+    const int n = (int)ua.size();
+    const int roles = t.kind == KIND_PAIR ? 2 : 3;
+    const int32_t* src = t.kind == KIND_PAIR ? hp.pairs.data() + 2ll * t.f_begin : hp.triplets.data() + 3ll * t.f_begin;
+    std::vector<int8_t> colour((size_t)n, -1);
+    int count[32] = {0};
+    int64_t collisions = 0;
+    int32_t members[32];
+    for (int g0 = 0; g0 < t.n_feat; g0 += 32) {
+        const int g1 = std::min(t.n_feat, g0 + 32);
+        for (int r = 0; r < roles; ++r) {
+            uint32_t used = 0;
+            int nm = 0;
+            for (int s = g0; s < g1; ++s) {
+                const int32_t a = (int32_t)(std::lower_bound(ua.begin(), ua.end(), src[(size_t)roles * s + r]) - ua.begin());
+                bool dup = false;
+                for (int m = 0; m < nm; ++m) dup |= members[m] == a;
+                if (dup) continue;                               // same atom = broadcast, no conflict
+                members[nm++] = a;
+                if (colour[a] >= 0) {
+                    if (used & (1u << colour[a])) ++collisions;
+                    used |= 1u << colour[a];
+                }
+            }
+            for (int m = 0; m < nm; ++m) {
+                const int32_t a = members[m];
+                if (colour[a] >= 0) continue;
+                int best = -1;
+                for (int cc = 0; cc < 32; ++cc)
+                    if (!(used & (1u << cc)) && (best < 0 || count[cc] < count[best])) best = cc;
+                if (best < 0) {                                  // cannot happen with <= 32 members; keep it total
+                    best = 0;
+                    for (int cc = 1; cc < 32; ++cc) if (count[cc] < count[best]) best = cc;
+                    ++collisions;
+                }
+                colour[a] = (int8_t)best; used |= 1u << best; ++count[best];
+            }
+        }
+    }
+    // rename the colours so that the fullest classes come first: the last row of the block is then filled from the left
+    int order[32], name[32];
+    for (int cc = 0; cc < 32; ++cc) order[cc] = cc;
+    std::stable_sort(order, order + 32, [&](int x, int y) { return count[x] > count[y]; });
+    for (int k = 0; k < 32; ++k) name[order[k]] = k;
+    int row[32] = {0};
+    slot_of.assign((size_t)n, 0);
+    n_slots = 0;
+    for (int i = 0; i < n; ++i) {                                // ua is sorted: each class stays sorted by atom index
+        const int cc = name[colour[i] < 0 ? 0 : colour[i]];
+        slot_of[i] = 32 * row[cc]++ + cc;
+        n_slots = std::max(n_slots, slot_of[i] + 1);
+    }
+    return collisions;
 }
 
 // Returns "" on success, otherwise the reason.
@@ -148,20 +213,27 @@ inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
         for (; k < u_pad_all; ++k) hp.src_off.insert(hp.src_off.end(), {3 * last, 3 * last + 1, 3 * last + 2});
     }
     int max_grp_floats = 0;
+    hp.bank_conflict_refs = 0;
+    std::vector<int32_t> slot_of;      // per-tile: slot of ua[i] inside the tile's staged block
     for (int c = 0; c < C; ++c) {
         TileDesc& t = hp.tiles[c];
         const std::vector<int32_t>& ua = tile_atoms[c];
+        auto rank = [&](int32_t atom) -> int32_t { return (int32_t)(std::lower_bound(ua.begin(), ua.end(), atom) - ua.begin()); };
         auto local = [&](int32_t atom) -> int32_t {
             if (hp.mode != CV_MODE_STAGED) return 3 * atom;
             if (shared_group) return 3 * global_slot[atom];
-            return 3 * (int32_t)(std::lower_bound(ua.begin(), ua.end(), atom) - ua.begin());
+            return 3 * slot_of[rank(atom)];
         };
         if (hp.mode == CV_MODE_STAGED && !shared_group) {
-            const int u_pad = round_up((int)ua.size(), 4);
+            int n_slots = 0;
+            hp.bank_conflict_refs += assign_bank_slots(hp, t, ua, slot_of, n_slots);
+            const int u_pad = round_up(n_slots, 4);
             t.grp_off = (int32_t)hp.src_off.size();
             t.grp_floats = 3 * u_pad;
+            std::vector<int32_t> atom_at((size_t)u_pad, ua.back());      // holes / padding repeat a valid atom
+            for (size_t i = 0; i < ua.size(); ++i) atom_at[slot_of[i]] = ua[i];
             for (int k = 0; k < u_pad; ++k) {
-                int32_t a = ua[std::min<size_t>(k, ua.size() - 1)];
+                const int32_t a = atom_at[k];
                 hp.src_off.insert(hp.src_off.end(), {3 * a, 3 * a + 1, 3 * a + 2});
             }
         } else if (hp.mode == CV_MODE_STAGED) {
@@ -240,6 +312,7 @@ inline void fill_info(const HostPlan& hp, CvPlanInfo& info) {
     info.boxrec_floats_per_frame = hp.desc.box_kind != CV_BOX_NONE ? kRecFloats : 0;
     info.workspace_bytes = kQueueBytes + (int64_t)hp.max_chunks * (hp.P + hp.A) * 24;
     const int64_t box_b = hp.desc.box_kind == CV_BOX_NONE ? 0 : (hp.desc.box_kind == CV_BOX_ORTHO ? 12 : 36);
+    info.gather_bank_conflicts = hp.bank_conflict_refs;
     info.algorithmic_bytes_per_frame = 12 * hp.n_distinct + box_b + 4 * hp.P + 4 * hp.A + 4 * hp.W + 4;
 }
 

@@ -96,6 +96,8 @@ typedef struct CvPlanInfo {
     int64_t  boxrec_floats_per_frame; /* floats per frame of a prepared box record */
     int64_t  workspace_bytes;         /* caller-provided scratch for caviar_run */
     int64_t  algorithmic_bytes_per_frame; /* 12U + box + 4P + 4A + 4*flag_words + 4 */
+    int64_t  gather_bank_conflicts;   /* staged mode: gather references the block layout could not keep off a used
+                                         shared-memory bank (0 = every warp gather is conflict-free) */
 } CvPlanInfo;
 
 /* Per-frame outputs of one caviar_run call (device pointers, any may be NULL). */

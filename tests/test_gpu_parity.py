@@ -403,3 +403,20 @@ def test_aggregates_are_bit_reproducible_run_to_run(cb):
     for r in runs[1:]:
         for a, b in zip(runs[0], r):
             assert torch.equal(a, b)
+
+
+def test_integration_md_ctypes_stub(cb, gold):
+    """The raw-ctypes binding INTEGRATION.md shows a maintainer (no caviar_b200 import on the call path)."""
+    import ctypes
+    import re
+    from caviar_b200.build import LIB_PATH
+    text = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "INTEGRATION.md")).read()
+    stub = re.search(r"```python\nimport ctypes, numpy as np\n(.*?)```", text, re.S).group(0)
+    code = stub.strip("`").replace("python\n", "", 1).replace("/path/to/libcaviar_b200.so", LIB_PATH)
+    ns = {}
+    exec(code, ns)
+    pairs = [(int(a), int(b)) for a, b in gold["C_pairs"]]              # includes negative indices
+    got = ns["compute_distances_parallel"](gold["C_x"], pairs)
+    assert _bits(got) == _bits(gold["C_d"])
+    got = ns["compute_distances_parallel"](gold["A_x"], [(int(a), int(b)) for a, b in gold["A_pairs"]])
+    assert _bits(got) == _bits(gold["A_d"])
