@@ -2,7 +2,9 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC cv_api.cu -o libcaviar_b200.so
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <mutex>
@@ -30,6 +32,21 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
         if (_e != cudaSuccess)                                                                     \
             return fail(CV_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));            \
     } while (0)
+
+// CAVIAR_TRACE=1: wall-clock of the host entry points' phases on stderr (development aid, off by default)
+namespace {
+struct Trace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    Trace() : on(std::getenv("CAVIAR_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[caviar_b200] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+}  // namespace
 
 extern "C" const char* caviar_last_error(void) { return g_err.c_str(); }
 extern "C" int caviar_abi_version(void) { return CV_ABI_VERSION; }
@@ -385,6 +402,7 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
     const bool in_pinned = is_pinned(xyz_host);
     const bool out_pinned = is_pinned(out->dist) && is_pinned(out->angle) && is_pinned(out->flags) && is_pinned(out->score);
 
+    Trace tr;
     HostCtx& hc = plan->host;
     std::lock_guard<std::mutex> lock(hc.mu);           // one host call per plan at a time
     HostSet (&set)[2] = hc.set;
@@ -418,6 +436,7 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
         CV_CUDA(cudaMemsetAsync(sq.p, 0, (size_t)F * 8, s_run.s));
     }
 
+    tr.mark("features_host: buffers");
     int64_t launches = 0;
     if (box_floats && n_frames > 0) {
         // boxes are tiny (<= 36 B per frame): upload and prepare all records once, outside the block loop
@@ -498,6 +517,7 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
         // waits for its download, which is ordered after its compute.
     }
     for (int k = 0; k < 2; ++k) { int rc = drain(k); if (rc != CV_OK) return rc; }
+    tr.mark("features_host: block loop");
     if (want_agg) {
         CV_CUDA(cudaStreamSynchronize(s_run.s));
         if (n_frames == 0) { memset(out->occupancy, 0, F * 8); memset(out->sum, 0, F * 8); memset(out->sumsq, 0, F * 8); }
@@ -511,23 +531,60 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
     return CV_OK;
 }
 
+// The reference calls its operator several times with the same pair list (trajectory A, trajectory B:
+// CAVIAR-1.0.py:337-338), so the last plan -- index tables on the device, the host entry point's device buffers,
+// bounce buffers, streams -- is kept between calls.  One entry; the mutex also serialises concurrent callers.
+namespace {
+struct OperatorCache {
+    std::mutex mu;
+    CvPlan* plan = nullptr;
+    int32_t n_atoms = 0;
+    int device = -1;
+    std::vector<int32_t> pairs;
+};
+OperatorCache& operator_cache() {
+    static OperatorCache* c = new OperatorCache();     // never destroyed: the CUDA runtime may be gone at exit
+    return *c;
+}
+}  // namespace
+
+extern "C" void caviar_release_cache(void) {
+    OperatorCache& oc = operator_cache();
+    std::lock_guard<std::mutex> lock(oc.mu);
+    if (oc.plan) { caviar_plan_destroy(oc.plan); oc.plan = nullptr; }
+    oc.pairs.clear(); oc.pairs.shrink_to_fit();
+}
+
 extern "C" int caviar_pair_distances_host(const float* xyz_host, int64_t n_frames, int32_t n_atoms,
                                           const int32_t* pairs, int64_t n_pairs, float* dist_host) {
     if (!dist_host && n_frames > 0) return fail(CV_E_INVALID, "null output");
-    CvPlanDesc d{};
-    d.struct_size = sizeof(CvPlanDesc);
-    d.n_atoms = n_atoms; d.n_pairs = n_pairs; d.pairs = pairs;
-    d.n_triplets = 0; d.triplets = nullptr;
-    d.box_kind = CV_BOX_NONE;
-    d.pair_cutoff = 0.0; d.hbond_dist_cutoff = 0.0; d.hbond_angle_cutoff = 0.0;
-    d.device = -1;
-    CvPlan* plan = nullptr;
-    int rc = caviar_plan_create(&d, &plan);
-    if (rc != CV_OK) return rc;
+    if (n_pairs > 0 && !pairs) return fail(CV_E_INVALID, "null index array");
+    Trace tr;
+    OperatorCache& oc = operator_cache();
+    std::lock_guard<std::mutex> lock(oc.mu);
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); cur = -1; }
+    const bool hit = oc.plan && oc.n_atoms == n_atoms && oc.device == cur && (int64_t)oc.pairs.size() == 2 * n_pairs &&
+                     (n_pairs == 0 || memcmp(oc.pairs.data(), pairs, (size_t)n_pairs * 8) == 0);
+    if (!hit) {
+        if (oc.plan) { caviar_plan_destroy(oc.plan); oc.plan = nullptr; }
+        CvPlanDesc d{};
+        d.struct_size = sizeof(CvPlanDesc);
+        d.n_atoms = n_atoms; d.n_pairs = n_pairs; d.pairs = pairs;
+        d.n_triplets = 0; d.triplets = nullptr;
+        d.box_kind = CV_BOX_NONE;
+        d.pair_cutoff = 0.0; d.hbond_dist_cutoff = 0.0; d.hbond_angle_cutoff = 0.0;
+        d.device = -1;
+        int rc = caviar_plan_create(&d, &oc.plan);
+        if (rc != CV_OK) { oc.plan = nullptr; return rc; }
+        oc.n_atoms = n_atoms; oc.device = oc.plan->device;
+        oc.pairs.assign(pairs, pairs + 2 * n_pairs);
+    }
+    tr.mark(hit ? "pair_distances: cached plan" : "pair_distances: plan_create");
     CvHostOutputs o{};
     o.dist = dist_host;
-    rc = caviar_features_host(plan, xyz_host, 3ll * n_atoms, nullptr, n_frames, &o, 0);
-    caviar_plan_destroy(plan);
+    int rc = caviar_features_host(oc.plan, xyz_host, 3ll * n_atoms, nullptr, n_frames, &o, 0);
+    tr.mark("pair_distances: features_host");
     return rc;
 }
 

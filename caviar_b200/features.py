@@ -6,6 +6,7 @@ device memory and streams; every computation happens in the sm_100a kernels behi
 from __future__ import annotations
 
 import ctypes as C
+import itertools
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
@@ -30,7 +31,18 @@ def _index_array(rows, width: int, n_atoms: int, what: str) -> np.ndarray:
     """(K, width) int32, C-contiguous; negative indices wrap like numpy fancy indexing (CAVIAR-1.0.py:118)."""
     if rows is None:
         return np.zeros((0, width), dtype=np.int32)
-    arr = np.asarray(rows)
+    arr = None
+    if type(rows) is list and rows and type(rows[0]) is tuple:
+        # the reference's own input: a long Python list of int tuples (CAVIAR-1.0.py:331).  np.asarray() spends
+        # 18 ms on 43 660 tuples; a flat iterator over verified plain ints takes half of that.
+        try:
+            if set(map(len, rows)) == {width} and set(map(type, itertools.chain.from_iterable(rows))) == {int}:
+                arr = np.fromiter(itertools.chain.from_iterable(rows), dtype=np.int64,
+                                  count=width * len(rows)).reshape(-1, width)
+        except (TypeError, OverflowError):
+            arr = None
+    if arr is None:
+        arr = np.asarray(rows)
     if arr.size == 0:
         return np.zeros((0, width), dtype=np.int32)
     if arr.ndim != 2 or arr.shape[1] != width:

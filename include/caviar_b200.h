@@ -166,10 +166,13 @@ int caviar_features_host(const CvPlan* plan, const float* xyz_host, int64_t fram
                          const float* box_host, int64_t n_frames, const CvHostOutputs* out,
                          int64_t frames_per_block /* 0 = auto */);
 
-/* compute_distances_parallel(X, pairs) in one call: builds a throw-away plan
- * (no box, no cut-offs) and fills dist_host [T][P].  CAVIAR-1.0.py:110-122. */
+/* compute_distances_parallel(X, pairs) in one call (no box, no cut-offs): fills dist_host [T][P].
+ * CAVIAR-1.0.py:110-122.  The plan and the device / bounce buffers of the LAST call are kept and reused when the
+ * next call brings the same n_atoms and pair list on the same device (the reference calls the operator once per
+ * trajectory with one list, :337-338); caviar_release_cache() frees them.  Thread-safe (calls are serialised). */
 int caviar_pair_distances_host(const float* xyz_host, int64_t n_frames, int32_t n_atoms,
                                const int32_t* pairs, int64_t n_pairs, float* dist_host);
+void caviar_release_cache(void);
 
 /* Host-side CSV row formatter for the Extractor output (CAVIAR_Distances-Extractor.py:147-151,196-198: one frame
  * column, then one distance column per pair).  Formats rows x cols float32 values as

@@ -80,3 +80,44 @@ def test_thresholds_match_double_compare():
         t = orc.f32_at_or_above(cut)
         for d in (np.nextafter(np.float32(cut), np.float32(0)), np.float32(cut), np.nextafter(np.float32(cut), np.float32(1e9))):
             assert (d < t) == (float(d) < cut)
+
+
+def test_index_array_fast_path_equals_numpy(cb):
+    """A list of plain-int tuples (the reference's pair list, CAVIAR-1.0.py:331) takes a flat-iterator path;
+    everything else goes through np.asarray -- same result, same errors."""
+    from caviar_b200.features import _index_array
+    pairs = [(i, j) for i in range(40) for j in range(i + 5, 40)]
+    a = _index_array(pairs, 2, 40, "pairs")
+    assert a.dtype == np.int32 and a.flags.c_contiguous
+    assert np.array_equal(a, np.asarray(pairs))
+    assert np.array_equal(_index_array([(-1, 0), (3, -40)], 2, 40, "pairs"), [[39, 0], [3, 0]])
+    assert np.array_equal(_index_array([(np.int64(1), 2)], 2, 40, "pairs"), [[1, 2]])       # slow path
+    assert np.array_equal(_index_array(np.asarray(pairs), 2, 40, "pairs"), a)
+    with pytest.raises(IndexError):
+        _index_array([(0, 40)], 2, 40, "pairs")
+    with pytest.raises(IndexError):
+        _index_array([(0.5, 1)], 2, 40, "pairs")
+    with pytest.raises(ValueError):
+        _index_array([(0, 1, 2)], 2, 40, "pairs")
+    with pytest.raises((ValueError, IndexError)):
+        _index_array([(0, 1), (2,)], 2, 40, "pairs")
+    with pytest.raises((IndexError, OverflowError)):
+        _index_array([(0, 2 ** 70)], 2, 40, "pairs")
+
+
+def test_staged_blocks_are_bank_conflict_free(cb):
+    """Planner: a tile's atoms are ordered so that the 32 lanes of every gather hit distinct shared-memory banks."""
+    rng = np.random.default_rng(3)
+    n = 20000
+    pairs = rng.integers(0, n, size=(5000, 2))
+    trips = rng.integers(0, n, size=(1000, 3))
+    info = cb.FeaturePlan(n, pairs, trips, box="triclinic", describe_only_sms=148).info
+    # greedy colouring: atoms shared between gathers may keep a few collisions (13 000 references here)
+    assert info["mode_name"] == "staged" and info["gather_bank_conflicts"] <= 40
+    once = rng.permutation(n)[:10000].reshape(-1, 2)       # every atom referenced once: always conflict-free
+    info = cb.FeaturePlan(n, once, None, box=None, force="staged", describe_only_sms=148).info
+    assert info["gather_bank_conflicts"] == 0
+    # heavy sharing (few atoms, many features) cannot always be conflict-free, but must still plan
+    pairs = rng.integers(0, 6000, size=(40000, 2))
+    info = cb.FeaturePlan(6000, pairs, None, box=None, force="staged", describe_only_sms=148).info
+    assert info["gather_bank_conflicts"] >= 0 and info["staged_floats_per_frame"] % 4 == 0

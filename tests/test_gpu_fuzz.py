@@ -1,0 +1,84 @@
+"""Randomised shape sweep of the sm_100a path against the oracle: ragged sizes, heavy atom sharing between features
+(the staged block layout has to keep shared atoms consistent across tiles), all box kinds, every plan mode; and the
+plan cache behind the reference operator (CAVIAR-1.0.py:337-338 call it with one list for two trajectories)."""
+import numpy as np
+import pytest
+
+from oracle import caviar_oracle as orc
+from test_gpu_parity import _bits, _check_features
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import caviar_b200
+    return caviar_b200
+
+
+def _cell(kind, L):
+    if kind == "ortho":
+        return np.diag([L, 1.1 * L, 0.9 * L])
+    # truncated octahedron in Amber's lower-triangular setting
+    return L * np.array([[1.0, 0.0, 0.0], [-1.0 / 3.0, 2.0 * np.sqrt(2.0) / 3.0, 0.0],
+                         [-1.0 / 3.0, -np.sqrt(2.0) / 3.0, np.sqrt(6.0) / 3.0]])
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_shapes_match_oracle(cb, seed):
+    rng = np.random.default_rng(9000 + seed)
+    box_kind = (None, "ortho", "triclinic")[seed % 3]
+    force = (None, "staged", "direct", None)[(seed // 3) % 4]
+    n = int(rng.choice([5, 31, 64, 257, 1000, 4099]))
+    T = int(rng.choice([1, 2, 3, 17, 70]))
+    P = int(rng.choice([0, 1, 31, 33, 895, 897, 2500]))
+    A = int(rng.choice([0, 1, 32, 225, 700]))
+    if P + A == 0:
+        P = 7
+    hot = max(2, n // int(rng.choice([1, 4, 50])))          # draw from a subset: many features share atoms
+    L = 30.0
+    cell = _cell(box_kind, L) if box_kind else None
+    base = rng.random((n, 3)) * L if cell is None else rng.random((n, 3)) @ cell
+    x = (base[None] + rng.normal(0, 0.4, size=(T, n, 3))).astype(np.float32)
+    pairs = rng.integers(0, hot, size=(P, 2))
+    triplets = rng.integers(0, hot, size=(A, 3))
+    if A:                                                    # some hydrogen-bond sized triplets
+        k = min(A, n // 3)
+        for t in range(k):
+            a, b, c = triplets[t]
+            x[:, b] = x[:, a] + rng.normal(0, 0.6, size=(T, 3)).astype(np.float32)
+            x[:, c] = x[:, b] + rng.normal(0, 1.2, size=(T, 3)).astype(np.float32)
+    box = None
+    if box_kind == "ortho":
+        box = np.broadcast_to(np.diag(cell).astype(np.float32), (T, 3)) * (1 + 1e-3 * np.arange(T, dtype=np.float32))[:, None]
+    elif box_kind == "triclinic":
+        box = np.broadcast_to(cell.astype(np.float32), (T, 3, 3)) * (1 + 1e-3 * np.arange(T, dtype=np.float32))[:, None, None]
+    cuts = (9.0, 6.0, 80.0)
+    with cb.FeaturePlan(n, pairs if P else None, triplets if A else None, box=box_kind, pair_cutoff=cuts[0],
+                        hbond_dist_cutoff=cuts[1], hbond_angle_cutoff=cuts[2], force=force) as plan:
+        res = plan.features_host(x, box, frames_per_block=int(rng.choice([0, 1, 5])))
+        info = plan.info
+    if info["mode_name"] == "staged":
+        assert info["gather_bank_conflicts"] >= 0
+    if not P:
+        res["dist"] = np.zeros((T, 0), np.float32)
+    if not A:
+        res["angle"] = np.zeros((T, 0), np.float32)
+    _check_features(cb, res, x, box, [tuple(p) for p in pairs], [tuple(t) for t in triplets], cuts, exact_dist=box_kind is None)
+
+
+def test_operator_plan_cache_switches_lists(cb):
+    """Same list twice (cache hit), another list (replaced), the first again; then an explicit release."""
+    from caviar_b200 import _lib
+    rng = np.random.default_rng(77)
+    xa = rng.normal(0, 20, size=(37, 50, 3)).astype(np.float32)
+    xb = rng.normal(0, 20, size=(11, 50, 3)).astype(np.float32)
+    xc = rng.normal(0, 20, size=(5, 64, 3)).astype(np.float32)
+    p1 = orc.all_pairs(50, 5)
+    p2 = [(int(a), int(b)) for a, b in rng.integers(0, 50, size=(len(p1), 2))]      # same length, other content
+    p3 = orc.all_pairs(64, 3)
+    for x, p in ((xa, p1), (xb, p1), (xa, p2), (xc, p3), (xb, p1)):
+        assert _bits(cb.compute_distances_parallel(x, p)) == _bits(orc.pair_distances(x, p, n_jobs=1))
+    _lib.lib.caviar_release_cache()
+    _lib.lib.caviar_release_cache()                           # idempotent
+    assert _bits(cb.compute_distances_parallel(xa, p1)) == _bits(orc.pair_distances(xa, p1, n_jobs=1))
