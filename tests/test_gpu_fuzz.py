@@ -82,3 +82,36 @@ def test_operator_plan_cache_switches_lists(cb):
     _lib.lib.caviar_release_cache()
     _lib.lib.caviar_release_cache()                           # idempotent
     assert _bits(cb.compute_distances_parallel(xa, p1)) == _bits(orc.pair_distances(xa, p1, n_jobs=1))
+
+
+@pytest.mark.parametrize("cfg_id,T", [(2, 2000), (3, 1000), (5, 200)])
+def test_survey_parity_sets_against_c_oracle(cb, cfg_id, T):
+    """SURVEY.md 8d parity sets at (close to) their full frame counts: affordable with the multi-threaded C oracle."""
+    from caviar_b200 import synthetic as syn
+    from oracle import c_oracle as co
+    top = syn.make_topology(cfg_id)
+    x = syn.parity_frames(top, T, only_referenced=True)
+    pairs, triplets = syn.compact_indices(top)
+    box = syn.boxes_for(top, T)
+    cuts = (8.0, 3.0, 135.0)
+    with cb.FeaturePlan(x.shape[1], pairs, triplets if len(triplets) else None, box=top.cfg.box, pair_cutoff=cuts[0],
+                        hbond_dist_cutoff=cuts[1], hbond_angle_cutoff=cuts[2]) as plan:
+        res = plan.features_host(x, box)
+    P, A = len(pairs), len(triplets)
+    d64 = co.pbc_pair_distances(x, pairs, box)
+    assert np.abs(res["dist"].astype(np.float64) - d64).max() <= 1e-4
+    fp, ft = cb.unpack_flags(res["flags"], P, A)
+    assert np.array_equal(fp, orc.contact_flags(res["dist"], cuts[0]))               # exact on the device's own features
+    near = orc.near_cutoff(d64, cuts[0], 1e-4)
+    assert np.array_equal(fp[~near], orc.contact_flags(d64, cuts[0])[~near])
+    assert near.mean() < 1e-3
+    flags_all = fp
+    if A:
+        a64, e64 = co.triplet_angles(x, triplets, box, with_end_distances=True)
+        assert np.abs(res["angle"].astype(np.float64) - a64).max() <= 1e-3
+        near_t = orc.near_cutoff(e64, cuts[1], 1e-4) | orc.near_cutoff(a64, cuts[2], 1e-3)
+        assert np.array_equal(ft[~near_t], orc.hbond_flags(e64, a64, cuts[1], cuts[2])[~near_t])
+        flags_all = np.concatenate([fp, ft], axis=1)
+    assert np.array_equal(res["score"], orc.frame_scores(flags_all))
+    assert np.array_equal(res["occupancy"], orc.occupancy(flags_all))
+    np.testing.assert_allclose(res["sum"][:P], res["dist"].astype(np.float64).sum(axis=0), rtol=1e-12)
