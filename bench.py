@@ -264,17 +264,17 @@ def main():
     S = int(info["staged_floats_per_frame"]) if info["mode_name"] == "staged" else 3 * U
     # ---- resident inputs: the rank's whole shard in the layout the fused kernel streams ----
     coords = torch.empty((T, S) if info["mode_name"] == "staged" else (T, U, 3), dtype=torch.float32, device=dev)
+    box_np = syn.boxes_for(top, T)
+    rec = plan.prepare_box(torch.from_numpy(box_np).to(dev)) if box_np is not None else None
     chunk = max(1, min(T, (1 << 30) // (U * 12)))
     for t0 in range(0, T, chunk):
         t1 = min(T, t0 + chunk)
         raw = syn.device_frames(top, t1 - t0, device=dev, seed=1000 * rank + t0, only_referenced=True)
         if info["mode_name"] == "staged":
-            plan.stage(raw, out=coords[t0:t1])
+            plan.stage(raw, None if rec is None else rec[t0:t1], out=coords[t0:t1])
         else:
             coords[t0:t1].copy_(raw)
     del raw
-    box_np = syn.boxes_for(top, T)
-    rec = plan.prepare_box(torch.from_numpy(box_np).to(dev)) if box_np is not None else None
     out = plan.alloc_outputs(T, device=dev)
     agg_f = torch.zeros((2, plan.F), dtype=torch.float64, device=dev)
     agg = cb.Aggregates(torch.zeros(plan.F, dtype=torch.int64, device=dev), agg_f[0], agg_f[1])
@@ -371,8 +371,8 @@ def main():
         with cb.FeaturePlan(cfg.n_atoms, top.pairs, top.triplets, box=cfg.box, **CUTS) as fplan:
             fws = fplan.new_workspace(dev)
             staged_buf = torch.empty((Td, int(fplan.info["staged_floats_per_frame"])), dtype=torch.float32, device=dev)
-            ms_stage = timed(lambda: fplan.stage(raw, out=staged_buf))
-            ms_both = timed(lambda: fplan.run(fplan.stage(raw, out=staged_buf), rec[:Td], out=out, aggregates=agg,
+            ms_stage = timed(lambda: fplan.stage(raw, None if rec is None else rec[:Td], out=staged_buf))
+            ms_both = timed(lambda: fplan.run(fplan.stage(raw, None if rec is None else rec[:Td], out=staged_buf), rec[:Td], out=out, aggregates=agg,
                                               workspace=fws, n_frames=Td))
             del staged_buf
         with cb.FeaturePlan(cfg.n_atoms, top.pairs, top.triplets, box=cfg.box, force="direct", **CUTS) as dplan:

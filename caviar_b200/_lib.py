@@ -42,7 +42,7 @@ class CvPlanInfo(C.Structure):
         ("n_features", C.c_int64), ("n_flag_words", C.c_int64), ("n_distinct_atoms", C.c_int64),
         ("staged_floats_per_frame", C.c_int64), ("boxrec_floats_per_frame", C.c_int64),
         ("workspace_bytes", C.c_int64), ("algorithmic_bytes_per_frame", C.c_int64),
-        ("gather_bank_conflicts", C.c_int64),
+        ("staged_fixedpoint_floats", C.c_int64), ("gather_bank_conflicts", C.c_int64),
     ]
 
     def as_dict(self):
@@ -71,7 +71,7 @@ SYMBOLS = {
     "caviar_plan_destroy": (None, [C.c_void_p]),
     "caviar_plan_info": (C.c_int, [C.c_void_p, C.POINTER(CvPlanInfo)]),
     "caviar_prepare_box": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
-    "caviar_stage_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "caviar_stage_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "caviar_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                              C.POINTER(CvFrameOutputs), C.POINTER(CvAggregates), C.c_void_p, C.c_void_p]),
     "caviar_last_launch_count": (C.c_int64, []),

@@ -232,23 +232,41 @@ extern "C" int caviar_prepare_box(const CvPlan* plan, const float* box_dev, int6
 }
 
 extern "C" int caviar_stage_frames(const CvPlan* plan, const float* xyz_dev, int64_t frame_stride_floats,
-                                   int64_t n_frames, float* staged_dev, void* stream) {
+                                   int64_t n_frames, float* staged_dev, const float* boxrec_dev, void* stream) {
     if (!plan) return fail(CV_E_INVALID, "null plan");
     g_launches = 0;
-    if (plan->hp.mode != CV_MODE_STAGED) return fail(CV_E_INVALID, "plan does not use the staged layout");
+    const HostPlan& hp = plan->hp;
+    if (hp.mode != CV_MODE_STAGED) return fail(CV_E_INVALID, "plan does not use the staged layout");
     if (n_frames <= 0) return CV_OK;
     if (!xyz_dev || !staged_dev) return fail(CV_E_INVALID, "null coordinate pointer");
-    if (frame_stride_floats < 3ll * plan->hp.desc.n_atoms) return fail(CV_E_INVALID, "frame stride smaller than 3*n_atoms");
+    if (frame_stride_floats < 3ll * hp.desc.n_atoms) return fail(CV_E_INVALID, "frame stride smaller than 3*n_atoms");
     if ((reinterpret_cast<uintptr_t>(staged_dev) & 15) != 0) return fail(CV_E_INVALID, "staged buffer must be 16-byte aligned");
-    const int S4 = (int)(plan->hp.staged_floats / 4);
+    const bool periodic = hp.desc.box_kind != CV_BOX_NONE;
+    if (periodic && !boxrec_dev)
+        return fail(CV_E_INVALID, "periodic plan: caviar_stage_frames needs the frames' box records (caviar_prepare_box) -- "
+                                  "atoms are wrapped into the cell and triplet blocks become fractional coordinates");
+    if (periodic) {
+        const int n_slots = (int)(hp.staged_floats / 3), first_frac = (int)(hp.frac_begin / 3);
+        const int per_block = 256 * kPeriodicAtomsPerThread;
+        for (int64_t t0 = 0; t0 < n_frames; t0 += 65535) {               // one block row per frame (grid.y <= 65535)
+            const int64_t n = std::min<int64_t>(65535, n_frames - t0);
+            stage_periodic_kernel<<<dim3((n_slots + per_block - 1) / per_block, (unsigned)n), 256, 0, (cudaStream_t)stream>>>(
+                xyz_dev + t0 * frame_stride_floats, frame_stride_floats, n, plan->d_src_off, n_slots, first_frac,
+                hp.staged_floats, boxrec_dev + t0 * kRecFloats, staged_dev + t0 * hp.staged_floats);
+            CV_CUDA(cudaGetLastError());
+            g_launches += 1;
+        }
+        return CV_OK;
+    }
+    const int S4 = (int)(hp.staged_floats / 4);
     const int64_t chunk = 65535ll * kStageFramesPerThread;     // grid.y is limited to 65535 blocks
     for (int64_t t0 = 0; t0 < n_frames; t0 += chunk) {
         const int64_t n = std::min<int64_t>(chunk, n_frames - t0);
-        dim3 grid((S4 + 255) / 256, (unsigned)((n + kStageFramesPerThread - 1) / kStageFramesPerThread));
-        stage_frames_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        const unsigned gy = (unsigned)((n + kStageFramesPerThread - 1) / kStageFramesPerThread);
+        stage_frames_kernel<<<dim3((S4 + 255) / 256, gy), 256, 0, (cudaStream_t)stream>>>(
             xyz_dev + t0 * frame_stride_floats, frame_stride_floats, n,
-            reinterpret_cast<const int4*>(plan->d_src_off), S4,
-            reinterpret_cast<float4*>(staged_dev + t0 * plan->hp.staged_floats));
+            reinterpret_cast<const int4*>(plan->d_src_off), S4, hp.staged_floats / 4,
+            reinterpret_cast<float4*>(staged_dev + t0 * hp.staged_floats));
         CV_CUDA(cudaGetLastError());
         g_launches += 1;
     }
@@ -489,7 +507,8 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
         CV_CUDA(cudaStreamWaitEvent(s_run.s, s.uploaded.e, 0));
         const float* coords = s.xyz.as<float>();
         if (hp.mode == CV_MODE_STAGED) {
-            rc = caviar_stage_frames(plan, s.xyz.as<float>(), frame_stride_floats, n, s.staged.as<float>(), s_run.s);
+            rc = caviar_stage_frames(plan, s.xyz.as<float>(), frame_stride_floats, n, s.staged.as<float>(),
+                                     box_floats ? rec_all.as<float>() + t0 * kRecFloats : nullptr, s_run.s);
             if (rc != CV_OK) return rc;
             launches += g_launches;
             coords = s.staged.as<float>();

@@ -11,6 +11,14 @@ constexpr int kTileWidth       = kConsumerThreads * kFeatPerThread;   // 896 fea
 constexpr int kMaxShifts       = 16;    // lattice translations the image search may have to try
 constexpr int kRecFloats       = 12 + 4 * kMaxShifts + kMaxShifts + 12;  // 104 floats = 416 B per frame
 constexpr int kMaxStages       = 8;
+// Periodic staged plans keep the blocks of their TRIPLET tiles as 32-bit fixed-point fractional coordinates.
+// CV_FRAC_PAIRS=1 does the same for the pair blocks (parity-green as well, same speed for orthorhombic cells, but
+// 2.5 % slower on config 3: long-range pairs of a triclinic cell still need the float32 reduce + search afterwards);
+// the default keeps pair blocks in float32, wrapped into the unit cell by K0.
+#ifndef CV_FRAC_PAIRS
+#define CV_FRAC_PAIRS 0
+#endif
+constexpr bool kFracPairs = CV_FRAC_PAIRS != 0;
 constexpr int kMaxGroupAtoms   = 21840; // 3*atom offsets stay below 65536 floats (256 KB) -- smem bound anyway
 
 // box record layout (floats)

@@ -29,6 +29,7 @@ struct HostPlan {
     std::vector<int32_t> idx0, idx1, idx2;
     std::vector<int32_t> src_off;      // staged float j of a frame <- float src_off[j] of the input frame
     int64_t staged_floats = 0;
+    int64_t frac_begin = 0;            // staged floats [frac_begin, staged_floats) are fixed-point fractional coordinates
     int64_t n_distinct = 0;
     int64_t bank_conflict_refs = 0;    // gather references left on an already-used shared-memory bank (staged mode)
     int frames_per_stage = 1, n_stages = 0, stage_floats = 0, smem_bytes = 0, whole_frame = 0;
@@ -189,14 +190,17 @@ inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
     const bool zc_ok = (d.n_atoms % 4 == 0) && frame_bytes <= 48 * 1024;
     if (d.flags & CV_PLAN_FORCE_DIRECT) hp.mode = CV_MODE_DIRECT;
     else if (d.flags & CV_PLAN_FORCE_STAGED) hp.mode = CV_MODE_STAGED;
-    else if (zc_ok && (int64_t)C * d.n_atoms <= 2 * sum_u + 1024) hp.mode = CV_MODE_ZEROCOPY;
+    // (periodic plans always go through K0: it wraps the atoms into the cell and turns triplet blocks into fixed point)
+    else if (zc_ok && d.box_kind == CV_BOX_NONE && (int64_t)C * d.n_atoms <= 2 * sum_u + 1024) hp.mode = CV_MODE_ZEROCOPY;
     else hp.mode = CV_MODE_STAGED;
 
     bool shared_group = false;
     int64_t u_pad_all = (hp.n_distinct + 3) / 4 * 4;
     if (hp.mode == CV_MODE_STAGED) {
         // one shared block when the tiles overlap heavily and the whole selection fits a stage
-        shared_group = (sum_u > hp.n_distinct + hp.n_distinct / 2) && (12 * u_pad_all <= 48 * 1024);
+        // (periodic plans stage the blocks of their triplet tiles as fractional fixed point: no block sharing there)
+        shared_group = (sum_u > hp.n_distinct + hp.n_distinct / 2) && (12 * u_pad_all <= 48 * 1024) &&
+                       !(d.box_kind != CV_BOX_NONE && hp.A > 0 && !kFracPairs);
     }
 
     // ---- index tables (float offsets = 3 * atom slot) and the staged layout ----
@@ -214,6 +218,7 @@ inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
     }
     int max_grp_floats = 0;
     hp.bank_conflict_refs = 0;
+    hp.frac_begin = -1;
     std::vector<int32_t> slot_of;      // per-tile: slot of ua[i] inside the tile's staged block
     for (int c = 0; c < C; ++c) {
         TileDesc& t = hp.tiles[c];
@@ -225,6 +230,10 @@ inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
             return 3 * slot_of[rank(atom)];
         };
         if (hp.mode == CV_MODE_STAGED && !shared_group) {
+            if ((t.kind == KIND_TRIPLET || kFracPairs) && d.box_kind != CV_BOX_NONE) {
+                t.reserved[0] = 1;                                    // fractional fixed-point block
+                if (hp.frac_begin < 0) hp.frac_begin = (int64_t)hp.src_off.size();
+            }
             int n_slots = 0;
             hp.bank_conflict_refs += assign_bank_slots(hp, t, ua, slot_of, n_slots);
             const int u_pad = round_up(n_slots, 4);
@@ -254,6 +263,8 @@ inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
         }
     }
     hp.staged_floats = (hp.mode == CV_MODE_STAGED) ? (int64_t)hp.src_off.size() : 0;
+    if (hp.mode == CV_MODE_STAGED && shared_group && d.box_kind != CV_BOX_NONE && kFracPairs) hp.frac_begin = 0;
+    if (hp.frac_begin < 0 || hp.mode != CV_MODE_STAGED) hp.frac_begin = hp.staged_floats;   // triplet tiles come last
     hp.whole_frame = (hp.mode == CV_MODE_ZEROCOPY) || (hp.mode == CV_MODE_STAGED && shared_group);
 
     // ---- pipeline geometry ----
@@ -313,6 +324,7 @@ inline void fill_info(const HostPlan& hp, CvPlanInfo& info) {
     info.workspace_bytes = kQueueBytes + (int64_t)hp.max_chunks * (hp.P + hp.A) * 24;
     const int64_t box_b = hp.desc.box_kind == CV_BOX_NONE ? 0 : (hp.desc.box_kind == CV_BOX_ORTHO ? 12 : 36);
     info.gather_bank_conflicts = hp.bank_conflict_refs;
+    info.staged_fixedpoint_floats = hp.staged_floats - hp.frac_begin;
     info.algorithmic_bytes_per_frame = 12 * hp.n_distinct + box_b + 4 * hp.P + 4 * hp.A + 4 * hp.W + 4;
 }
 

@@ -182,8 +182,12 @@ class FeaturePlan:
         check(_lib.lib.caviar_prepare_box(self._handle, b.data_ptr(), b.shape[0], rec.data_ptr(), self._stream_ptr()))
         return rec
 
-    def stage(self, xyz, out=None):
-        """K0: (T, N, 3) CUDA float32 frames -> staged (T, S) layout.  Identity for non-staged plans."""
+    def stage(self, xyz, boxrec=None, out=None):
+        """K0: (T, N, 3) CUDA float32 frames -> staged (T, S) layout.  Identity for non-staged plans.
+
+        A periodic plan needs ``boxrec = prepare_box(box)`` of the same frames: K0 translates atoms into the unit
+        cell and stores the atoms of triplet tiles as fixed-point fractional coordinates
+        (``info["staged_fixedpoint_floats"]``)."""
         import torch
         if self.mode != MODE_STAGED:
             return xyz
@@ -195,8 +199,11 @@ class FeaturePlan:
         S = int(self.info["staged_floats_per_frame"])
         if out is None:
             out = torch.empty((T, S), dtype=torch.float32, device=xyz.device)
+        if boxrec is not None and (boxrec.shape[0] < T or not boxrec.is_contiguous()):
+            raise ValueError("boxrec must hold one contiguous record per staged frame")
         check(_lib.lib.caviar_stage_frames(self._handle, xyz.data_ptr(), xyz.stride(0) if T > 1 else 3 * self.n_atoms,
-                                           T, out.data_ptr(), self._stream_ptr()))
+                                           T, out.data_ptr(), None if boxrec is None else boxrec.data_ptr(),
+                                           self._stream_ptr()))
         return out
 
     def new_aggregates(self, device="cuda") -> Aggregates:

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define CV_ABI_VERSION 1
+#define CV_ABI_VERSION 2
 
 /* status codes */
 #define CV_OK              0
@@ -96,6 +96,8 @@ typedef struct CvPlanInfo {
     int64_t  boxrec_floats_per_frame; /* floats per frame of a prepared box record */
     int64_t  workspace_bytes;         /* caller-provided scratch for caviar_run */
     int64_t  algorithmic_bytes_per_frame; /* 12U + box + 4P + 4A + 4*flag_words + 4 */
+    int64_t  staged_fixedpoint_floats; /* trailing part of a staged frame that holds the atoms of the TRIPLET tiles of a
+                                         periodic plan as 32-bit fixed-point fractional coordinates (0 = none) */
     int64_t  gather_bank_conflicts;   /* staged mode: gather references the block layout could not keep off a used
                                          shared-memory bank (0 = every warp gather is conflict-free) */
 } CvPlanInfo;
@@ -131,9 +133,13 @@ int caviar_prepare_box(const CvPlan* plan, const float* box_dev, int64_t n_frame
                        float* boxrec_dev, void* stream);
 
 /* Compaction (CV_MODE_STAGED only): frames (device, frame t at xyz + t*stride
- * floats, AoS xyz) -> staged layout (device, staged_floats_per_frame each). */
+ * floats, AoS xyz) -> staged layout (device, staged_floats_per_frame each).
+ * A periodic plan needs the frames' box records (boxrec_dev from caviar_prepare_box, same
+ * frames): atoms outside the unit cell are translated into it, and the atoms of triplet
+ * tiles are stored as 32-bit fixed-point fractional coordinates
+ * (CvPlanInfo.staged_fixedpoint_floats).  Plans without a box take boxrec_dev = NULL. */
 int caviar_stage_frames(const CvPlan* plan, const float* xyz_dev, int64_t frame_stride_floats,
-                        int64_t n_frames, float* staged_dev, void* stream);
+                        int64_t n_frames, float* staged_dev, const float* boxrec_dev, void* stream);
 
 /* The fused hot path over n_frames frames resident on the device.
  *   coords: CV_MODE_STAGED -> the staged buffer; otherwise the frames themselves

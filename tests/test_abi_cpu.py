@@ -23,7 +23,7 @@ def test_header_symbols_all_exported(cb):
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(_lib.lib, name)
-    assert _lib.lib.caviar_abi_version() == 1
+    assert _lib.lib.caviar_abi_version() == 2
 
 
 def test_no_cpu_fallback(cb):
@@ -121,3 +121,22 @@ def test_staged_blocks_are_bank_conflict_free(cb):
     pairs = rng.integers(0, 6000, size=(40000, 2))
     info = cb.FeaturePlan(6000, pairs, None, box=None, force="staged", describe_only_sms=148).info
     assert info["gather_bank_conflicts"] >= 0 and info["staged_floats_per_frame"] % 4 == 0
+
+
+def test_periodic_triplet_tiles_are_staged_as_fixed_point(cb):
+    """Periodic plan with triplets: always the staged layout, triplet blocks (the tail of a staged frame) in 32-bit
+    fixed-point fractional coordinates; no box or no triplets: plain float32 blocks."""
+    rng = np.random.default_rng(8)
+    n = 256                                                     # small, aligned frames: zero-copy candidates
+    pairs = rng.integers(0, n, size=(4000, 2))
+    trips = rng.integers(0, n, size=(500, 3))
+    info = cb.FeaturePlan(n, pairs, trips, box="ortho", describe_only_sms=148).info
+    assert info["mode_name"] == "staged" and info["staged_fixedpoint_floats"] > 0
+    assert info["staged_fixedpoint_floats"] % 12 == 0 and info["staged_fixedpoint_floats"] < info["staged_floats_per_frame"]
+    assert cb.FeaturePlan(n, pairs, trips, box=None, describe_only_sms=148).info["staged_fixedpoint_floats"] == 0
+    only_p = cb.FeaturePlan(n, pairs, None, box="triclinic", describe_only_sms=148).info
+    assert only_p["staged_fixedpoint_floats"] == 0 and only_p["mode_name"] == "staged"     # periodic: never zero-copy
+    assert cb.FeaturePlan(n, pairs, None, box=None, describe_only_sms=148).info["mode_name"] == "zerocopy"
+    only_t = cb.FeaturePlan(n, None, trips, box="triclinic", describe_only_sms=148).info
+    assert only_t["staged_fixedpoint_floats"] == only_t["staged_floats_per_frame"]
+    assert cb.FeaturePlan(n, pairs, trips, box="ortho", force="direct", describe_only_sms=148).info["staged_fixedpoint_floats"] == 0

@@ -115,3 +115,40 @@ def test_survey_parity_sets_against_c_oracle(cb, cfg_id, T):
     assert np.array_equal(res["score"], orc.frame_scores(flags_all))
     assert np.array_equal(res["occupancy"], orc.occupancy(flags_all))
     np.testing.assert_allclose(res["sum"][:P], res["dist"].astype(np.float64).sum(axis=0), rtol=1e-12)
+
+
+def test_fixed_point_staging_needs_box_records(cb):
+    import torch
+    rng = np.random.default_rng(1)
+    n, T = 64, 5
+    x = torch.from_numpy((rng.random((T, n, 3)) * 20).astype(np.float32)).cuda()
+    box = torch.full((T, 3), 20.0, device="cuda")
+    trips = rng.integers(0, n, size=(40, 3))
+    with cb.FeaturePlan(n, [(0, 1)], trips, box="ortho") as plan:
+        assert plan.info["staged_fixedpoint_floats"] > 0
+        with pytest.raises(cb.CaviarError):
+            plan.stage(x)                                       # no box records: refused, not guessed
+        rec = plan.prepare_box(box)
+        out = plan.run(plan.stage(x, rec), rec)
+        want = orc.triplet_angles(x.cpu().numpy(), trips, np.full((T, 3), 20.0))
+        assert np.abs(out.angle.cpu().numpy() - want).max() <= 1e-3
+
+
+def test_unwrapped_coordinates_far_outside_the_cell(cb):
+    """Molecules that diffused many box lengths away (unwrapped trajectories): fractional staging wraps them exactly."""
+    rng = np.random.default_rng(2)
+    n, T, L = 96, 7, 25.0
+    base = rng.random((n, 3)) * L
+    x = base[None] + rng.normal(0, 0.3, size=(T, n, 3))
+    x += rng.integers(-40, 40, size=(1, n, 3)) * L             # every atom in its own distant image
+    x = x.astype(np.float32)
+    pairs = rng.integers(0, n, size=(300, 2))
+    trips = rng.integers(0, n, size=(100, 3))
+    box = np.full((T, 3), L)
+    with cb.FeaturePlan(n, pairs, trips, box="ortho", pair_cutoff=6.0, hbond_dist_cutoff=7.0, hbond_angle_cutoff=70.0) as plan:
+        res = plan.features_host(x, box)
+    a64 = orc.triplet_angles(x, trips, box)
+    d64 = orc.pbc_pair_distances(x, pairs, box)
+    # float32 INPUT at |x| ~ 1000 A carries 6e-5 A of quantisation; the path itself adds nothing visible on top
+    assert np.abs(res["dist"] - d64).max() <= 1e-4
+    assert np.abs(res["angle"] - a64).max() <= 1e-3

@@ -273,7 +273,7 @@ def test_device_path_matches_host_path_and_accumulates(cb):
         host = plan.features_host(x, box)
         xd = torch.from_numpy(x).cuda()
         rec = plan.prepare_box(torch.from_numpy(box).cuda())
-        staged = plan.stage(xd)
+        staged = plan.stage(xd, rec)
         agg = plan.new_aggregates()
         ws = plan.new_workspace()
         out1 = plan.run(staged[:40], rec[:40], aggregates=agg, workspace=ws)
@@ -301,17 +301,18 @@ def test_size_independent_properties_at_scale(cb):
     box = torch.from_numpy(syn.boxes_for(top, T)).cuda()
     with cb.FeaturePlan(x.shape[1], pairs, triplets, box="triclinic") as plan:
         rec = plan.prepare_box(box)
-        staged = plan.stage(x)
+        staged = plan.stage(x, rec)
         agg = plan.new_aggregates()
         out = plan.run(staged, rec, aggregates=agg)
         # translating every atom by a lattice vector must not change anything beyond float32 rounding
         shift = torch.from_numpy((top.cell[1] - top.cell[2]).astype(np.float32)).cuda()
         x2 = x.clone()
         x2[:, ::3] += shift * box[:, None, 0, 0:1] / float(top.cell[0, 0])
-        out_b = plan.run(plan.stage(x2), rec)
+        out_b = plan.run(plan.stage(x2, rec), rec)
         # swapping (i, j) must not change any distance bit
         with cb.FeaturePlan(x.shape[1], pairs[:, ::-1].copy(), triplets[:, ::-1].copy(), box="triclinic") as plan_r:
-            out_r = plan_r.run(plan_r.stage(x), plan_r.prepare_box(box))
+            rec_r = plan_r.prepare_box(box)
+            out_r = plan_r.run(plan_r.stage(x, rec_r), rec_r)
         torch.cuda.synchronize()
     P, A = len(pairs), len(triplets)
     fl = out.flags.cpu().numpy().view(np.uint32)
@@ -393,7 +394,8 @@ def test_aggregates_are_bit_reproducible_run_to_run(cb):
     x = syn.device_frames(top, T)
     box = torch.from_numpy(syn.boxes_for(top, T)).cuda()
     with cb.FeaturePlan(x.shape[1], pairs, triplets, box="triclinic") as plan:
-        rec, staged = plan.prepare_box(box), plan.stage(x)
+        rec = plan.prepare_box(box)
+        staged = plan.stage(x, rec)
         runs = []
         for _ in range(3):
             agg = plan.new_aggregates()

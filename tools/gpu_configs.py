@@ -14,9 +14,9 @@ for cfg_id, T in ((1, 1000), (2, 10000), (3, 32768), (4, 2048), (5, 4096)):
     U = len(top.referenced)
     raw = syn.device_frames(top, T, only_referenced=True)
     with cb.FeaturePlan(U, pairs, triplets if len(triplets) else None, box=top.cfg.box) as plan:
-        coords = plan.stage(raw)
         b = syn.boxes_for(top, T)
         rec = plan.prepare_box(torch.from_numpy(b).cuda()) if b is not None else None
+        coords = plan.stage(raw, rec)
         out = plan.alloc_outputs(T)
         agg = plan.new_aggregates()
         for _ in range(3):

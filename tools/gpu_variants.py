@@ -17,7 +17,6 @@ for name, box, prs, trs in (("tric_full", "triclinic", pairs, triplets), ("tric_
                             ("tric_trip", "triclinic", None, triplets), ("ortho_full", "ortho", pairs, triplets),
                             ("none_full", None, pairs, triplets), ("none_pairs", None, pairs, None)):
     plan = cb.FeaturePlan(U, prs, trs, box=box)
-    staged = plan.stage(raw)
     if box == "triclinic":
         b = torch.from_numpy(syn.boxes_for(top, T)).cuda()
     elif box == "ortho":
@@ -25,6 +24,7 @@ for name, box, prs, trs in (("tric_full", "triclinic", pairs, triplets), ("tric_
     else:
         b = None
     rec = plan.prepare_box(b) if b is not None else None
+    staged = plan.stage(raw, rec)
     out = plan.alloc_outputs(T)
     agg = plan.new_aggregates()
     for _ in range(3):
