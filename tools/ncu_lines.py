@@ -53,7 +53,8 @@ def main():
     print(f"total warp-instructions {tot_i}, samples {tot_s}")
     for loc, (n, s, ops) in sorted(per_line.items(), key=lambda kv: -kv[1][0])[:60]:
         top = ",".join(f"{k}:{v * 100 // max(n, 1)}" for k, v in sorted(ops.items(), key=lambda kv: -kv[1])[:4])
-        t = text.get(loc[1], "")[:90] if loc else ""
+        same_file = bool(loc) and bool(srcfile) and loc[0] == srcfile.split("/")[-1]
+        t = text.get(loc[1], "")[:90] if same_file else ("(inlined CUDA header intrinsic)" if loc else "")
         print(f"{100 * n / tot_i:5.1f}% inst {100 * s / max(tot_s, 1):5.1f}% stall  {loc}  [{top}]  {t.strip()}")
 
 
