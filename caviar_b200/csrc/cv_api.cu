@@ -347,7 +347,12 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
         const int64_t tf = cf / 4;
         int64_t n_big = (3 * n_frames / 4) / cf;
         int64_t n_small = (n_frames - n_big * cf + tf - 1) / tf;
-        if (tf < kMinChunkFrames || n_big + n_small > hp.max_chunks) {      // short run: uniform chunks
+        // Short runs (tail items below kMinChunkFrames frames): every item costs a flush of 24 B per feature and a
+        // pipeline restart, so the small tail only pays when a CTA gets so few items that imbalance dominates
+        // (config 2: 4 items per CTA, +4 %; config 5 at 4 096 frames: 16 per CTA, -3.5 % -> uniform chunks there).
+        const int64_t uniform_items = (n_frames + cf - 1) / cf * (int64_t)hp.tiles.size();
+        const bool small_tail_pays = uniform_items < 8ll * hp.n_ctas;
+        if (tf < kMinTailFrames || (tf < kMinChunkFrames && !small_tail_pays) || n_big + n_small > hp.max_chunks) {
             n_big = (n_frames + cf - 1) / cf; n_small = 0;
         }
         rp.chunk_frames = (int32_t)cf;
