@@ -235,6 +235,11 @@ def main():
         raise SystemExit("bench.py needs a B200: caviar_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = None
+    if world > 1:
+        # one process per GPU: keep this rank's threads and page-locked buffers on the GPU's own NUMA node
+        from caviar_b200.sharding import bind_to_gpu_numa_node
+        numa_node = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL writes its version banner to stdout (C level) when the communicator comes up; rank 0's stdout must
@@ -481,7 +486,8 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(cfg, T, P, A, U, plan=info, l2="inputs (%.1f GB per rank) >> 126 MB L2, no flush needed"
                                           % (coords_bytes(T, S) / 1e9), setup_s=round(t_setup, 1),
-                                          parallelism=f"frame-sharded x{world}, one NCCL all-reduce of aggregates per step"),
+                                          parallelism=f"frame-sharded x{world}, one NCCL all-reduce of aggregates per step",
+                                          rank0_numa_node=numa_node),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
                 "gpu_launches": launches_per_step * args.steps, "raw_frame_input": direct,
                 "reference_native_shape": native, "full_size_check": full_check}

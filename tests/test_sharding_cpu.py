@@ -77,3 +77,14 @@ def test_two_rank_reduce_matches_single_process():
     s1, s2 = orc.moment_sums(d)
     np.testing.assert_allclose(sums[0], s1, rtol=1e-14)
     np.testing.assert_allclose(sums[1], s2, rtol=1e-14)
+
+
+def test_numa_binding_helper_is_a_no_op_without_topology():
+    from caviar_b200.sharding import _parse_cpulist, bind_to_gpu_numa_node
+    assert _parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert _parse_cpulist("") == []
+    import os
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa_node(0) is None or isinstance(bind_to_gpu_numa_node(0), int)      # no GPU here: None
+    if bind_to_gpu_numa_node(0) is None:
+        assert os.sched_getaffinity(0) == before
