@@ -276,9 +276,9 @@ extern "C" int caviar_stage_frames(const CvPlan* plan, const float* xyz_dev, int
 // ------------------------------------------------------------------------------------------------
 // the fused run
 // ------------------------------------------------------------------------------------------------
-template <int BOX, bool PIPE>
+template <int BOX, bool PIPE, bool FRAC>
 static cudaError_t launch_features(const CvPlan* plan, const RunParams& rp, cudaStream_t st) {
-    auto kern = features_kernel<BOX, PIPE>;
+    auto kern = features_kernel<BOX, PIPE, FRAC>;
     const int threads = PIPE ? kConsumerThreads + kProducerThreads : kConsumerThreads;
     const int smem = PIPE ? plan->hp.smem_bytes : 0;
     if (PIPE) {
@@ -372,14 +372,20 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
     if (rp.score) CV_CUDA(cudaMemsetAsync(rp.score, 0, sizeof(int32_t) * n_frames, st));
 
     cudaError_t e;
-    const bool pipe = hp.mode != CV_MODE_DIRECT;
-    switch (hp.desc.box_kind * 2 + (pipe ? 1 : 0)) {
-        case 0: e = launch_features<0, false>(plan, rp, st); break;
-        case 1: e = launch_features<0, true>(plan, rp, st); break;
-        case 2: e = launch_features<1, false>(plan, rp, st); break;
-        case 3: e = launch_features<1, true>(plan, rp, st); break;
-        case 4: e = launch_features<2, false>(plan, rp, st); break;
-        default: e = launch_features<2, true>(plan, rp, st); break;
+    // TMA ring unless the plan gathers from global memory (raw frames, or K0's compact frame of a large overlapping
+    // selection); staged periodic plans carry fixed-point triplet blocks
+    const bool pipe = hp.mode != CV_MODE_DIRECT && !hp.gather_global;
+    const bool frac = hp.mode == CV_MODE_STAGED && hp.desc.box_kind != CV_BOX_NONE;
+    switch (hp.desc.box_kind * 4 + (pipe ? 2 : 0) + (frac ? 1 : 0)) {
+        case 0: e = launch_features<0, false, false>(plan, rp, st); break;
+        case 2: e = launch_features<0, true, false>(plan, rp, st); break;
+        case 4: e = launch_features<1, false, false>(plan, rp, st); break;
+        case 5: e = launch_features<1, false, true>(plan, rp, st); break;
+        case 7: e = launch_features<1, true, true>(plan, rp, st); break;
+        case 8: e = launch_features<2, false, false>(plan, rp, st); break;
+        case 9: e = launch_features<2, false, true>(plan, rp, st); break;
+        case 11: e = launch_features<2, true, true>(plan, rp, st); break;
+        default: return fail(CV_E_INVALID, "internal: no kernel flavour for this plan");
     }
     if (e != cudaSuccess) return fail(CV_E_CUDA, std::string("features_kernel launch: ") + cudaGetErrorString(e));
     g_launches += 1;

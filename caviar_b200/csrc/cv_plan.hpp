@@ -29,6 +29,7 @@ struct HostPlan {
     std::vector<int32_t> idx0, idx1, idx2;
     std::vector<int32_t> src_off;      // staged float j of a frame <- float src_off[j] of the input frame
     int64_t staged_floats = 0;
+    bool gather_global = false;        // staged, but the kernel gathers with LDG from the compact staged frame (no TMA ring)
     int64_t frac_begin = 0;            // staged floats [frac_begin, staged_floats) are fixed-point fractional coordinates
     int64_t n_distinct = 0;
     int64_t bank_conflict_refs = 0;    // gather references left on an already-used shared-memory bank (staged mode)
@@ -186,21 +187,42 @@ inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
     for (uint8_t s : seen) hp.n_distinct += s;
 
     // ---- how do coordinates reach the SMs? ----
+    // Three cases.  (1) Tiles that share few atoms get one coordinate block each (staged, TMA-streamed; an atom is
+    // duplicated once per tile that references it).  (2) Tiles that overlap heavily -- all-pairs lists: every tile of
+    // 896 columns needs ~900 atoms of the same selection -- share ONE block: the frame itself (zero-copy) or the
+    // compacted selection, TMA-streamed whole while it is small.  (3) Beyond ~16 KB the whole-block refill per tile
+    // and frame costs more than it saves (measured: all pairs of 3 000 / 5 000 atoms run 1.3x / 1.9x faster gathered
+    // with LDG through L1/L2 than through a 36 / 60 KB whole-frame ring), so large overlapping selections are
+    // gathered from global memory: from the caller's frames without a box, from K0's compact wrapped / fixed-point
+    // frame with one (hp.gather_global).  Per-tile blocks for such lists would multiply the frame thousands of times.
     const int64_t frame_bytes = 12ll * d.n_atoms;
-    const bool zc_ok = (d.n_atoms % 4 == 0) && frame_bytes <= 48 * 1024;
-    if (d.flags & CV_PLAN_FORCE_DIRECT) hp.mode = CV_MODE_DIRECT;
-    else if (d.flags & CV_PLAN_FORCE_STAGED) hp.mode = CV_MODE_STAGED;
-    // (periodic plans always go through K0: it wraps the atoms into the cell and turns triplet blocks into fixed point)
-    else if (zc_ok && d.box_kind == CV_BOX_NONE && (int64_t)C * d.n_atoms <= 2 * sum_u + 1024) hp.mode = CV_MODE_ZEROCOPY;
-    else hp.mode = CV_MODE_STAGED;
-
+    const int64_t u_pad_all = (hp.n_distinct + 3) / 4 * 4;
+    constexpr int64_t kWholeBlockBytes = 16 * 1024;
+    const bool periodic = d.box_kind != CV_BOX_NONE;
+    const bool heavy = sum_u > hp.n_distinct + hp.n_distinct / 2;
+    const bool small_all = 12 * u_pad_all <= kWholeBlockBytes;
+    // per-tile blocks would multiply the input bytes by more than ~8 (moderate sharing, e.g. random lists over few
+    // atoms, is better served by per-tile blocks than by uncoalesced LDG gathers: 7x faster on config 3)
+    const bool blow_up = sum_u > 8 * (hp.n_distinct + 1024);
+    const bool one_kind_block = !(periodic && hp.A > 0 && !kFracPairs);   // float pair atoms and fixed-point triplet atoms cannot share
+    const bool zc_ok = !periodic && (d.n_atoms % 4 == 0) && frame_bytes <= (C <= 2 ? 48 * 1024 : kWholeBlockBytes);
     bool shared_group = false;
-    int64_t u_pad_all = (hp.n_distinct + 3) / 4 * 4;
-    if (hp.mode == CV_MODE_STAGED) {
-        // one shared block when the tiles overlap heavily and the whole selection fits a stage
-        // (periodic plans stage the blocks of their triplet tiles as fractional fixed point: no block sharing there)
-        shared_group = (sum_u > hp.n_distinct + hp.n_distinct / 2) && (12 * u_pad_all <= 48 * 1024) &&
-                       !(d.box_kind != CV_BOX_NONE && hp.A > 0 && !kFracPairs);
+    hp.gather_global = false;
+    if (d.flags & CV_PLAN_FORCE_DIRECT) {
+        hp.mode = CV_MODE_DIRECT;
+    } else if (d.flags & CV_PLAN_FORCE_STAGED) {
+        hp.mode = CV_MODE_STAGED;
+        shared_group = heavy && small_all && one_kind_block;
+    } else if (zc_ok && ((int64_t)C * d.n_atoms <= 2 * sum_u + 1024 || (heavy && 4 * hp.n_distinct >= 3ll * d.n_atoms))) {
+        hp.mode = CV_MODE_ZEROCOPY;          // tiles need most of the (small) frame anyway: stream it as it is
+    } else if (heavy && small_all && one_kind_block) {
+        hp.mode = CV_MODE_STAGED; shared_group = true;
+    } else if (blow_up && !periodic) {
+        hp.mode = CV_MODE_DIRECT;
+    } else if (blow_up) {
+        hp.mode = CV_MODE_STAGED; hp.gather_global = true;
+    } else {
+        hp.mode = CV_MODE_STAGED;
     }
 
     // ---- index tables (float offsets = 3 * atom slot) and the staged layout ----
@@ -208,7 +230,24 @@ inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
     hp.idx1.assign((size_t)C * kTileWidth, 0);
     hp.idx2.assign((size_t)C * kTileWidth, 0);
     hp.src_off.clear();
-    std::vector<int32_t> global_slot;
+    std::vector<int32_t> global_slot, pair_slot, trip_slot;
+    int32_t trip_block_off = 0, pair_block_floats = 0, trip_block_floats = 0;
+    if (hp.gather_global) {
+        // one compact block per kind: [atoms of the pair tiles][atoms of the triplet tiles], each sorted by atom index
+        auto compact = [&](const std::vector<int32_t>& refs, std::vector<int32_t>& slot) -> int32_t {
+            std::vector<uint8_t> used((size_t)d.n_atoms, 0);
+            for (int32_t v : refs) used[v] = 1;
+            slot.assign((size_t)d.n_atoms, -1);
+            int32_t k = 0, last = -1;
+            for (int32_t a = 0; a < d.n_atoms; ++a)
+                if (used[a]) { slot[a] = k++; last = a; hp.src_off.insert(hp.src_off.end(), {3 * a, 3 * a + 1, 3 * a + 2}); }
+            for (; last >= 0 && k % 4 != 0; ++k) hp.src_off.insert(hp.src_off.end(), {3 * last, 3 * last + 1, 3 * last + 2});
+            return 3 * k;
+        };
+        pair_block_floats = compact(hp.pairs, pair_slot);
+        trip_block_off = pair_block_floats;
+        trip_block_floats = compact(hp.triplets, trip_slot);
+    }
     if (hp.mode == CV_MODE_STAGED && shared_group) {
         global_slot.assign((size_t)d.n_atoms, -1);
         int32_t k = 0, last = 0;
@@ -226,10 +265,19 @@ inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
         auto rank = [&](int32_t atom) -> int32_t { return (int32_t)(std::lower_bound(ua.begin(), ua.end(), atom) - ua.begin()); };
         auto local = [&](int32_t atom) -> int32_t {
             if (hp.mode != CV_MODE_STAGED) return 3 * atom;
+            if (hp.gather_global) return 3 * (t.kind == KIND_PAIR ? pair_slot[atom] : trip_slot[atom]);
             if (shared_group) return 3 * global_slot[atom];
             return 3 * slot_of[rank(atom)];
         };
-        if (hp.mode == CV_MODE_STAGED && !shared_group) {
+        if (hp.gather_global) {
+            const bool trip = t.kind == KIND_TRIPLET;
+            t.grp_off = trip ? trip_block_off : 0;
+            t.grp_floats = trip ? trip_block_floats : pair_block_floats;
+            if (trip || kFracPairs) {
+                t.reserved[0] = 1;
+                if (hp.frac_begin < 0) hp.frac_begin = kFracPairs ? 0 : trip_block_off;
+            }
+        } else if (hp.mode == CV_MODE_STAGED && !shared_group) {
             if ((t.kind == KIND_TRIPLET || kFracPairs) && d.box_kind != CV_BOX_NONE) {
                 t.reserved[0] = 1;                                    // fractional fixed-point block
                 if (hp.frac_begin < 0) hp.frac_begin = (int64_t)hp.src_off.size();
@@ -268,7 +316,7 @@ inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
     hp.whole_frame = (hp.mode == CV_MODE_ZEROCOPY) || (hp.mode == CV_MODE_STAGED && shared_group);
 
     // ---- pipeline geometry ----
-    if (hp.mode == CV_MODE_DIRECT) {
+    if (hp.mode == CV_MODE_DIRECT || hp.gather_global) {
         hp.frames_per_stage = 1; hp.n_stages = 0; hp.stage_floats = 0; hp.smem_bytes = 0; hp.occupancy = 2;
     } else {
         const int gb = max_grp_floats * 4;
@@ -311,7 +359,7 @@ inline void fill_info(const HostPlan& hp, CvPlanInfo& info) {
     info.mode = hp.mode;
     info.n_tiles = (int)hp.tiles.size();
     info.n_ctas = hp.n_ctas;
-    info.threads_per_cta = kConsumerThreads + (hp.mode == CV_MODE_DIRECT ? 0 : kProducerThreads);
+    info.threads_per_cta = kConsumerThreads + ((hp.mode == CV_MODE_DIRECT || hp.gather_global) ? 0 : kProducerThreads);
     info.stages = hp.n_stages;
     info.frames_per_stage = hp.frames_per_stage;
     info.smem_bytes = hp.smem_bytes;

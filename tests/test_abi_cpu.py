@@ -67,10 +67,17 @@ def test_plan_describe_configs(cb, cfg_id, mode):
 
 def test_plan_forced_modes_and_direct(cb):
     rng = np.random.default_rng(0)
-    pairs = rng.integers(0, 4096, size=(5000, 2))
+    pairs = rng.integers(0, 4096, size=(1000, 2))              # two tiles that share few atoms
     for force, mode in (("direct", "direct"), ("staged", "staged"), (None, "staged")):
         info = cb.FeaturePlan(4096, pairs, None, describe_only_sms=148, force=force).info
         assert info["mode_name"] == mode
+    # six tiles that each touch a third of a 48-KB frame: per-tile blocks (2.4x the bytes) beat uncoalesced gathers
+    pairs = rng.integers(0, 4096, size=(5000, 2))
+    assert cb.FeaturePlan(4096, pairs, None, describe_only_sms=148).info["mode_name"] == "staged"
+    # ... of a 12-KB frame: stream the frame as it is
+    pairs = rng.integers(0, 1024, size=(5000, 2))
+    assert cb.FeaturePlan(1024, pairs, None, describe_only_sms=148).info["mode_name"] == "zerocopy"
+    assert cb.FeaturePlan(1024, pairs, None, box="ortho", describe_only_sms=148).info["mode_name"] == "staged"
 
 
 def test_thresholds_match_double_compare():
@@ -140,3 +147,24 @@ def test_periodic_triplet_tiles_are_staged_as_fixed_point(cb):
     only_t = cb.FeaturePlan(n, None, trips, box="triclinic", describe_only_sms=148).info
     assert only_t["staged_fixedpoint_floats"] == only_t["staged_floats_per_frame"]
     assert cb.FeaturePlan(n, pairs, trips, box="ortho", force="direct", describe_only_sms=148).info["staged_fixedpoint_floats"] == 0
+
+
+def test_large_overlapping_selections_do_not_blow_up_the_staged_layout(cb):
+    """All pairs of thousands of atoms: every tile needs ~900 atoms of the same frame.  Per-tile blocks would stage
+    the frame thousands of times over; the planner must share one block (<= 100 KB) or gather directly."""
+    def rows_against_all(n):                                      # every 50th atom against every atom, i-major
+        i = np.repeat(np.arange(0, n, 50), n)
+        return np.stack([i, np.tile(np.arange(n), len(i) // n)], 1).astype(np.int32)
+
+    for n, want in ((1000, "zerocopy"), (1001, "staged"), (3000, "direct"), (9000, "direct")):
+        pairs = rows_against_all(n)
+        info = cb.FeaturePlan(n, pairs, None, box=None, describe_only_sms=148).info
+        assert info["mode_name"] == want, (n, info)
+        assert info["staged_floats_per_frame"] <= 3 * (n + 3)
+    pairs = rows_against_all(5000)
+    trips = np.stack([np.arange(0, 300), np.arange(1, 301), np.arange(2, 302)], 1)
+    info = cb.FeaturePlan(5000, pairs, trips, box="triclinic", describe_only_sms=148).info
+    assert info["mode_name"] == "staged" and info["stages"] == 0 and info["smem_bytes"] == 0       # LDG from K0's compact frame
+    assert info["staged_floats_per_frame"] <= 3 * (5000 + 304 + 8) and info["staged_fixedpoint_floats"] == 3 * 304
+    info = cb.FeaturePlan(5000, pairs, None, box="ortho", describe_only_sms=148).info
+    assert info["mode_name"] == "staged" and info["staged_floats_per_frame"] <= 3 * 5004     # periodic: compact frame via K0

@@ -152,3 +152,44 @@ def test_unwrapped_coordinates_far_outside_the_cell(cb):
     # float32 INPUT at |x| ~ 1000 A carries 6e-5 A of quantisation; the path itself adds nothing visible on top
     assert np.abs(res["dist"] - d64).max() <= 1e-4
     assert np.abs(res["angle"] - a64).max() <= 1e-3
+
+
+@pytest.mark.parametrize("n,box,A,mode,stages", [(1000, None, 0, "zerocopy", 2), (3000, None, 0, "direct", 0),
+                                                   (5000, "ortho", 0, "staged", 0), (1000, "triclinic", 64, "staged", 0),
+                                                   (5000, "triclinic", 200, "staged", 0), (9000, None, 0, "direct", 0)])
+def test_large_overlapping_selection_modes(cb, n, box, A, mode, stages):
+    """Rows of a big all-pairs list: per-tile blocks would multiply the frame hundreds of times.  Small frames are
+    streamed whole; large ones are gathered from global memory -- from the caller's frames (no box) or from K0's
+    compact wrapped / fixed-point frame (periodic: mode 'staged' without a TMA ring)."""
+    from oracle import c_oracle as co
+    rng = np.random.default_rng(n + A)
+    rows = np.arange(7, n, 211 if n > 1000 else 37)
+    pairs = np.stack([np.repeat(rows, n), np.tile(np.arange(n), len(rows))], 1).astype(np.int32)
+    trips = rng.integers(0, n, size=(A, 3)) if A else None
+    T, L = 6, 80.0
+    cell = None
+    if box == "ortho":
+        cell = np.full((T, 3), L)
+    elif box == "triclinic":
+        cell = np.broadcast_to(orc.box_matrix([L, L, L], [109.4712206] * 3), (T, 3, 3)).copy()
+    x = (rng.random((T, n, 3)) * L).astype(np.float32)
+    x[:, ::5] += np.float32(3 * L)                              # some atoms a few cells away
+    cuts = (10.0, 30.0, 60.0)
+    with cb.FeaturePlan(n, pairs, trips, box=box, pair_cutoff=cuts[0], hbond_dist_cutoff=cuts[1], hbond_angle_cutoff=cuts[2]) as plan:
+        assert plan.info["mode_name"] == mode and plan.info["stages"] == stages
+        res = plan.features_host(x, cell, want=("dist", "angle", "flags", "score", "agg"))
+    if box is None:
+        assert _bits(res["dist"]) == _bits(orc.pair_distances_f32_steps(x, pairs[:, 0], pairs[:, 1]))
+    else:
+        assert np.abs(res["dist"] - co.pbc_pair_distances(x, pairs, cell)).max() <= 1e-4
+    fp, ft = cb.unpack_flags(res["flags"], len(pairs), A)
+    assert np.array_equal(fp, orc.contact_flags(res["dist"], cuts[0]))
+    flags = fp
+    if A:
+        a64, e64 = co.triplet_angles(x, trips, cell, with_end_distances=True)
+        assert np.abs(res["angle"] - a64).max() <= 1e-3
+        near = orc.near_cutoff(e64, cuts[1], 1e-4) | orc.near_cutoff(a64, cuts[2], 1e-3)
+        assert np.array_equal(ft[~near], orc.hbond_flags(e64, a64, cuts[1], cuts[2])[~near])
+        flags = np.concatenate([fp, ft], axis=1)
+    assert np.array_equal(res["occupancy"], flags.sum(axis=0).astype(np.uint64))
+    assert np.array_equal(res["score"], flags.sum(axis=1).astype(np.int32))
