@@ -72,6 +72,7 @@ SYMBOLS = {
     "caviar_plan_info": (C.c_int, [C.c_void_p, C.POINTER(CvPlanInfo)]),
     "caviar_prepare_box": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "caviar_stage_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "caviar_plan_status": (C.c_int, [C.c_void_p, C.c_void_p]),
     "caviar_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                              C.POINTER(CvFrameOutputs), C.POINTER(CvAggregates), C.c_void_p, C.c_void_p]),
     "caviar_last_launch_count": (C.c_int64, []),

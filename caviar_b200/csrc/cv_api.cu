@@ -188,8 +188,8 @@ extern "C" int caviar_plan_create(const CvPlanDesc* desc, CvPlan** out) {
     if (e == cudaSuccess) e = upload(&p->d_idx1, p->hp.idx1);
     if (e == cudaSuccess) e = upload(&p->d_idx2, p->hp.idx2);
     if (e == cudaSuccess) e = upload(&p->d_src_off, p->hp.src_off);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_err, sizeof(int));
-    if (e == cudaSuccess) e = cudaMemset(p->d_err, 0, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_err, 2 * sizeof(int));      // [0] box set-up, [1] staging (sticky)
+    if (e == cudaSuccess) e = cudaMemset(p->d_err, 0, 2 * sizeof(int));
     if (e != cudaSuccess) {
         std::string msg = std::string("plan upload: ") + cudaGetErrorString(e);
         caviar_plan_destroy(p);
@@ -252,7 +252,7 @@ extern "C" int caviar_stage_frames(const CvPlan* plan, const float* xyz_dev, int
             const int64_t n = std::min<int64_t>(65535, n_frames - t0);
             stage_periodic_kernel<<<dim3((n_slots + per_block - 1) / per_block, (unsigned)n), 256, 0, (cudaStream_t)stream>>>(
                 xyz_dev + t0 * frame_stride_floats, frame_stride_floats, n, plan->d_src_off, n_slots, first_frac,
-                hp.staged_floats, boxrec_dev + t0 * kRecFloats, staged_dev + t0 * hp.staged_floats);
+                hp.staged_floats, boxrec_dev + t0 * kRecFloats, staged_dev + t0 * hp.staged_floats, plan->d_err + 1);
             CV_CUDA(cudaGetLastError());
             g_launches += 1;
         }
@@ -269,6 +269,20 @@ extern "C" int caviar_stage_frames(const CvPlan* plan, const float* xyz_dev, int
             reinterpret_cast<float4*>(staged_dev + t0 * hp.staged_floats));
         CV_CUDA(cudaGetLastError());
         g_launches += 1;
+    }
+    return CV_OK;
+}
+
+// Sticky staging errors (set asynchronously by K0): synchronises `stream`, reports and clears them.
+extern "C" int caviar_plan_status(const CvPlan* plan, void* stream) {
+    if (!plan) return fail(CV_E_INVALID, "null plan");
+    int err = 0;
+    CV_CUDA(cudaMemcpyAsync(&err, plan->d_err + 1, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CV_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (err) {
+        CV_CUDA(cudaMemsetAsync(plan->d_err + 1, 0, sizeof(int), (cudaStream_t)stream));
+        return fail(CV_E_INVALID, "non-finite coordinate in an atom of a triplet (periodic plans stage those as fixed-point "
+                                  "fractional coordinates, which cannot carry NaN / Inf): the angles of the affected frames are meaningless");
     }
     return CV_OK;
 }
@@ -557,6 +571,10 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
     }
     CV_CUDA(cudaStreamSynchronize(s_run.s));
     quiesce.armed = false;
+    if (hp.mode == CV_MODE_STAGED && box_floats && hp.frac_begin < hp.staged_floats) {
+        int rc = caviar_plan_status(plan, s_run.s);
+        if (rc != CV_OK) return rc;
+    }
     g_launches = launches;
     return CV_OK;
 }

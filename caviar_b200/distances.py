@@ -29,6 +29,11 @@ def _result_array(n_frames: int, n_pairs: int) -> np.ndarray:
     return np.empty((n_frames, n_pairs), dtype=np.float32)
 
 
+def release_cache() -> None:
+    """Free the plan and the device / bounce buffers the operator keeps between calls (``caviar_release_cache``)."""
+    _lib.lib.caviar_release_cache()
+
+
 def compute_distances_parallel(X_xyz, pairs, n_jobs=None, chunk_size=8000):
     """(T, n, 3) coordinates and a sequence of (i, j) -> (T, P) distances.
 

@@ -206,6 +206,10 @@ class FeaturePlan:
                                            self._stream_ptr()))
         return out
 
+    def check(self):
+        """Synchronise the current stream and raise if K0 met a NaN / Inf coordinate it had to stage as fixed point."""
+        check(_lib.lib.caviar_plan_status(self._handle, self._stream_ptr()))
+
     def new_aggregates(self, device="cuda") -> Aggregates:
         import torch
         return Aggregates(torch.zeros(self.F, dtype=torch.int64, device=device),

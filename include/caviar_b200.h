@@ -141,6 +141,11 @@ int caviar_prepare_box(const CvPlan* plan, const float* box_dev, int64_t n_frame
 int caviar_stage_frames(const CvPlan* plan, const float* xyz_dev, int64_t frame_stride_floats,
                         int64_t n_frames, float* staged_dev, const float* boxrec_dev, void* stream);
 
+/* caviar_stage_frames is asynchronous; what it can only find out on the device -- a NaN / Inf coordinate in an atom
+ * that is staged as fixed point -- is kept as a sticky flag on the plan.  This call synchronises `stream`, returns
+ * CV_E_INVALID if the flag is set, and clears it.  (caviar_features_host checks it itself.) */
+int caviar_plan_status(const CvPlan* plan, void* stream);
+
 /* The fused hot path over n_frames frames resident on the device.
  *   coords: CV_MODE_STAGED -> the staged buffer; otherwise the frames themselves
  *           (frame_stride_floats apart; CV_MODE_ZEROCOPY needs stride == 3*n_atoms).

@@ -193,3 +193,30 @@ def test_large_overlapping_selection_modes(cb, n, box, A, mode, stages):
         flags = np.concatenate([fp, ft], axis=1)
     assert np.array_equal(res["occupancy"], flags.sum(axis=0).astype(np.uint64))
     assert np.array_equal(res["score"], flags.sum(axis=1).astype(np.int32))
+
+
+def test_non_finite_triplet_coordinates_are_reported(cb):
+    """NaN in, NaN out on the float paths; the fixed-point triplet blocks cannot carry a NaN, so K0 flags it."""
+    import torch
+    n, T = 32, 4
+    rng = np.random.default_rng(3)
+    x = (rng.random((T, n, 3)) * 20).astype(np.float32)
+    x[2, 5, 1] = np.nan
+    box = np.full((T, 3), 20.0)
+    with cb.FeaturePlan(n, [(5, 6), (1, 2)], None, box="ortho") as plan:          # pairs only: NaN propagates
+        d = plan.features_host(x, box, want=("dist",))["dist"]
+        assert np.isnan(d[2, 0]) and np.isfinite(np.delete(d.ravel(), 4)).all()
+    with cb.FeaturePlan(n, [(1, 2)], [(4, 5, 6), (7, 8, 9)], box="ortho") as plan:
+        with pytest.raises(cb.CaviarError, match="non-finite"):
+            plan.features_host(x, box)
+        res = plan.features_host(np.nan_to_num(x), box)                            # the flag was cleared
+        assert np.isfinite(res["angle"]).all()
+        xd = torch.from_numpy(x).cuda()
+        rec = plan.prepare_box(torch.from_numpy(box.astype(np.float32)).cuda())
+        plan.stage(xd, rec)
+        with pytest.raises(cb.CaviarError, match="non-finite"):
+            plan.check()
+        plan.check()                                                                # cleared again
+    with cb.FeaturePlan(n, None, [(4, 5, 6)], box=None) as plan:                   # no box: float path, NaN propagates
+        assert np.isnan(plan.features_host(x, want=("angle",))["angle"][2, 0])
+    cb.release_cache()
