@@ -220,3 +220,34 @@ def test_non_finite_triplet_coordinates_are_reported(cb):
     with cb.FeaturePlan(n, None, [(4, 5, 6)], box=None) as plan:                   # no box: float path, NaN propagates
         assert np.isnan(plan.features_host(x, want=("angle",))["angle"][2, 0])
     cb.release_cache()
+
+
+def test_outputs_beyond_2_31_elements(cb):
+    """Maximum sizes: a (T, P) distance matrix of 2.5e9 elements (9.9 GB) -- row offsets need 64 bits everywhere."""
+    import torch
+    if torch.cuda.mem_get_info()[0] < 40 << 30:
+        pytest.skip("needs 40 GB of free device memory")
+    n, T = 1000, 5003
+    pairs = orc.all_pairs(n, 5)
+    P = len(pairs)
+    assert T * P > 2 ** 31
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = (torch.rand((T, n, 3), device="cuda", generator=g) * 60.0).contiguous()
+    with cb.FeaturePlan(n, pairs, None, box=None, pair_cutoff=8.0) as plan:
+        out = plan.alloc_outputs(T, want=("dist", "flags", "score"))
+        agg = plan.new_aggregates()
+        plan.run(x, None, out=out, aggregates=agg)
+        torch.cuda.synchronize()
+    ii, jj = np.asarray(pairs)[:, 0], np.asarray(pairs)[:, 1]
+    for t in (0, 2171, 4334, T - 1):                      # rows on both sides of element 2^31 (row 4334) and the last one
+        want = orc.pair_distances_f32_steps(x[t:t + 1].cpu().numpy(), ii, jj)
+        assert _bits(out.dist[t].cpu().numpy()) == _bits(want[0])
+        fp, _ = cb.unpack_flags(out.flags[t:t + 1].cpu().numpy(), P, 0)
+        assert np.array_equal(fp[0], orc.contact_flags(want, 8.0)[0])
+        assert int(out.score[t]) == int(fp.sum())
+    thr = float(orc.f32_at_or_above(8.0))
+    occ = torch.zeros(P, dtype=torch.int64, device="cuda")
+    for t0 in range(0, T, 512):                           # the device's own distances, in slices
+        occ += (out.dist[t0:t0 + 512] < thr).sum(dim=0)
+    assert torch.equal(occ, agg.occupancy)
+    assert int(out.score.sum()) == int(occ.sum())
