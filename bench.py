@@ -320,10 +320,11 @@ def main():
     clocks = sampler.stop()
     total_ms = ev[0][0].elapsed_time(ev[-1][2])
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in ev]))
-    tm = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device=dev)
+    reduce_ms = float(np.mean([b.elapsed_time(c) for _, b, c in ev]))      # the one exchange step (0 at N = 1)
+    tm = torch.tensor([total_ms, kern_ms, reduce_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    total_ms, kern_ms = float(tm[0]), float(tm[1])
+    total_ms, kern_ms, reduce_ms = float(tm[0]), float(tm[1]), float(tm[2])
     ms_per_step = total_ms / args.steps
     evals_per_step = world * T * (P + A)
     value = evals_per_step / (ms_per_step * 1e-3)
@@ -489,7 +490,10 @@ def main():
                                           parallelism=f"frame-sharded x{world}, one NCCL all-reduce of aggregates per step",
                                           rank0_numa_node=numa_node),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-                "gpu_launches": launches_per_step * args.steps, "raw_frame_input": direct,
+                "gpu_launches": launches_per_step * args.steps,
+                "exchange": {"what": "NCCL sum all-reduce of occupancy i64[F] + {sum, sumsq} f64[2F] (24*F bytes)",
+                             "bytes": 24 * plan.F, "ms_per_step": reduce_ms if world > 1 else 0.0},
+                "raw_frame_input": direct,
                 "reference_native_shape": native, "full_size_check": full_check}
         print(json.dumps(line), flush=True)
     if world > 1:
