@@ -310,6 +310,33 @@ def min_image(delta: np.ndarray, box) -> np.ndarray:
     return best
 
 
+def min_image_gap(delta: np.ndarray, box) -> np.ndarray:
+    """Length difference between the two SHORTEST images of every displacement, (T, K), fp64 (inf without a box).
+
+    A displacement within a rounding error of a Voronoi face of the lattice has two images of (nearly) the same
+    length: its distance is well defined, but WHICH image is "the minimum" -- and with it the direction of the
+    vector, hence an angle built on it -- is not.  The parity tests use this to set aside image-ambiguous arms."""
+    delta = np.asarray(delta, dtype=np.float64)
+    h = _as_box_matrices(box, delta.shape[0])
+    if h is None:
+        return np.full(delta.shape[:2], np.inf)
+    frac = np.einsum('tkc,tcd->tkd', delta, np.linalg.inv(h))
+    frac -= np.rint(frac)
+    lens = np.stack([np.sqrt(np.einsum('tkc,tkc->tk', c, c))
+                     for c in (np.einsum('tkc,tcd->tkd', frac + s, h) for s in _IMAGE_SHIFTS)], axis=0)
+    lens.sort(axis=0)
+    return lens[1] - lens[0]
+
+
+def triplet_arm_gaps(coords, triplets, box=None) -> np.ndarray:
+    """min_image_gap of both arms of every triplet, the smaller of the two: (T, A)."""
+    c = np.asarray(coords, dtype=np.float64)
+    idx = np.asarray(triplets, dtype=np.int64).reshape(-1, 3)
+    gu = min_image_gap(c[:, idx[:, 0], :] - c[:, idx[:, 1], :], box)
+    gv = min_image_gap(c[:, idx[:, 2], :] - c[:, idx[:, 1], :], box)
+    return np.minimum(gu, gv)
+
+
 def pbc_pair_distances(coords, pairs, box=None) -> np.ndarray:
     """fp64 minimum-image distances, (T, P).  With ``box=None`` plain Euclidean."""
     c = np.asarray(coords, dtype=np.float64)

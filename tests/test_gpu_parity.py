@@ -116,9 +116,15 @@ def _check_features(cb, res, x, box, pairs, triplets, cuts, exact_dist=False):
             assert _bits(res["dist"]) == _bits(orc.pair_distances_f32_steps(x, ii, jj))
         err = np.abs(res["dist"].astype(np.float64) - d64)
         assert err.max() <= DIST_TOL, f"distance error {err.max():.3g} A"
+    amb = np.zeros((T, A), dtype=bool)
     if A:
+        # An arm within a rounding error of a Voronoi face of the lattice has two images of the same length to
+        # within the distance tolerance: its direction -- and the angle -- is not defined at float32 resolution
+        # (one such arm in 2e7 of the random-shape sweep).  Those are set aside, and there must be next to none.
+        amb = orc.triplet_arm_gaps(x, triplets, box) < DIST_TOL
+        assert amb.mean() <= 1e-3
         err = np.abs(res["angle"].astype(np.float64) - a64)
-        assert err.max() <= ANGLE_TOL, f"angle error {err.max():.3g} deg"
+        assert err[~amb].max(initial=0.0) <= ANGLE_TOL, f"angle error {err[~amb].max():.3g} deg"
     fp, ft = cb.unpack_flags(res["flags"], P, A)
     # the flags the device reports must equal the double-compare of ITS OWN float32 features (bit-exact) ...
     if P:
@@ -128,7 +134,7 @@ def _check_features(cb, res, x, box, pairs, triplets, cuts, exact_dist=False):
     near_p = orc.near_cutoff(d64, pc, DIST_TOL)
     assert np.array_equal(fp[~near_p], want_p[~near_p])
     want_t = orc.hbond_flags(dac64, a64, hd, ha)
-    near_t = orc.near_cutoff(dac64, hd, DIST_TOL) | orc.near_cutoff(a64, ha, ANGLE_TOL)
+    near_t = orc.near_cutoff(dac64, hd, DIST_TOL) | orc.near_cutoff(a64, ha, ANGLE_TOL) | amb
     assert np.array_equal(ft[~near_t], want_t[~near_t])
     # integer aggregates are exact functions of the flags
     flags_all = np.concatenate([fp, ft], axis=1)

@@ -193,3 +193,13 @@ def test_flags_occupancy_scores_packing():
     s1, s2 = orc.moment_sums(d)
     assert np.allclose(s1 / 37, d.mean(0), rtol=1e-6)
     assert np.allclose(s2, (d.astype(np.float64) ** 2).sum(0), rtol=1e-14)
+
+
+def test_min_image_gap_flags_displacements_on_a_voronoi_face():
+    L = 20.0
+    d = np.array([[[10.0, 1.0, 2.0], [9.0, 1.0, 2.0], [3.0, 0.0, 0.0]]])          # exactly half a box, 1 A off, short
+    gap = orc.min_image_gap(d, np.array([L, L, L]))
+    assert gap[0, 0] == 0.0 and gap[0, 1] == pytest.approx(np.sqrt(11 ** 2 + 5) - np.sqrt(9 ** 2 + 5)) and gap[0, 2] > 10
+    assert np.isinf(orc.min_image_gap(d, None)).all()
+    x = np.zeros((1, 3, 3)); x[0, 0] = (10.0, 0, 0); x[0, 2] = (0, 3.0, 0)
+    assert orc.triplet_arm_gaps(x, [(0, 1, 2)], np.array([L, L, L]))[0, 0] == 0.0
