@@ -19,7 +19,6 @@ constexpr int kMaxStages       = 8;
 #define CV_FRAC_PAIRS 0
 #endif
 constexpr bool kFracPairs = CV_FRAC_PAIRS != 0;
-constexpr int kMaxGroupAtoms   = 21840; // 3*atom offsets stay below 65536 floats (256 KB) -- smem bound anyway
 
 // box record layout (floats)
 enum : int {
