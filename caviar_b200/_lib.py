@@ -61,7 +61,8 @@ class CvAggregates(C.Structure):
 
 class CvHostOutputs(C.Structure):
     _fields_ = [("dist", C.c_void_p), ("angle", C.c_void_p), ("flags", C.c_void_p), ("score", C.c_void_p),
-                ("occupancy", C.c_void_p), ("sum", C.c_void_p), ("sumsq", C.c_void_p)]
+                ("occupancy", C.c_void_p), ("sum", C.c_void_p), ("sumsq", C.c_void_p),
+                ("weights_q32", C.c_void_p), ("score_q32", C.c_void_p)]
 
 
 # every symbol include/caviar_b200.h declares: (restype, argtypes)
@@ -76,6 +77,7 @@ SYMBOLS = {
     "caviar_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                              C.POINTER(CvFrameOutputs), C.POINTER(CvAggregates), C.c_void_p, C.c_void_p]),
     "caviar_last_launch_count": (C.c_int64, []),
+    "caviar_weighted_scores": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "caviar_features_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                        C.POINTER(CvHostOutputs), C.c_int64]),
     "caviar_pair_distances_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),

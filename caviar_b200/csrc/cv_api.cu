@@ -116,13 +116,13 @@ bool is_pinned(const void* p) {
 }
 // Everything caviar_features_host needs between calls: allocated on first use, grown on demand, freed with the plan.
 struct HostSet {
-    DevBuf xyz, staged, dist, angle, flags, score;
-    PinBuf h_in, h_dist, h_angle, h_flags, h_score;
+    DevBuf xyz, staged, dist, angle, flags, score, wscore;
+    PinBuf h_in, h_dist, h_angle, h_flags, h_score, h_wscore;
     Event uploaded, computed, downloaded;
 };
 struct HostCtx {
     HostSet set[2];
-    DevBuf ws, occ, sum, sq, box_all, rec_all;
+    DevBuf ws, occ, sum, sq, box_all, rec_all, wq;
     Stream s_up, s_run, s_down;
     std::mutex mu;
 };
@@ -413,6 +413,24 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
     return CV_OK;
 }
 
+extern "C" int caviar_weighted_scores(const CvPlan* plan, const uint32_t* flags_dev, int64_t n_frames,
+                                      const int64_t* weights_q32_dev, int64_t* score_q32_dev, void* stream) {
+    g_launches = 0;
+    if (!plan) return fail(CV_E_INVALID, "null plan");
+    if (n_frames < 0) return fail(CV_E_INVALID, "negative frame count");
+    if (n_frames == 0) return CV_OK;
+    if (!flags_dev || !weights_q32_dev || !score_q32_dev) return fail(CV_E_INVALID, "null argument");
+    const HostPlan& hp = plan->hp;
+    const long long blocks = (n_frames * 32 + 255) / 256;
+    if (blocks > 0x7fffffffll) return fail(CV_E_INVALID, "too many frames for one call");
+    weighted_score_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        flags_dev, n_frames, hp.W, hp.Wp, hp.P, reinterpret_cast<const long long*>(weights_q32_dev),
+        reinterpret_cast<long long*>(score_q32_dev));
+    CV_CUDA(cudaGetLastError());
+    g_launches = 1;
+    return CV_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // reference-facing host entry points
 // ------------------------------------------------------------------------------------------------
@@ -435,21 +453,25 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
     if (frame_stride_floats < 3ll * hp.desc.n_atoms) return fail(CV_E_INVALID, "frame stride smaller than 3*n_atoms");
     const bool want_agg = out->occupancy || out->sum || out->sumsq;
     if (want_agg && !(out->occupancy && out->sum && out->sumsq)) return fail(CV_E_INVALID, "aggregates are all-or-none");
+    const bool want_ws = out->score_q32 != nullptr;
+    if (want_ws && !out->weights_q32) return fail(CV_E_INVALID, "score_q32 needs weights_q32");
+    const bool need_flags = out->flags || want_ws;          // the weighted scores are computed from the flag words
     CV_CUDA(cudaSetDevice(plan->device));
 
     // block size: ~256 MB of input + output per buffer set
     const int64_t in_row = frame_stride_floats * 4 + box_floats * 4;
-    const int64_t out_row = (out->dist ? 4 * P : 0) + (out->angle ? 4 * A : 0) + (out->flags ? 4 * W : 0) + (out->score ? 4 : 0);
+    const int64_t out_row = (out->dist ? 4 * P : 0) + (out->angle ? 4 * A : 0) + (out->flags ? 4 * W : 0) + (out->score ? 4 : 0) + (want_ws ? 8 : 0);
     int64_t TB = frames_per_block > 0 ? frames_per_block : std::max<int64_t>(64, (256ll << 20) / std::max<int64_t>(1, in_row + out_row));
     TB = std::max<int64_t>(1, std::min<int64_t>(TB, std::max<int64_t>(n_frames, 1)));
     const bool in_pinned = is_pinned(xyz_host);
-    const bool out_pinned = is_pinned(out->dist) && is_pinned(out->angle) && is_pinned(out->flags) && is_pinned(out->score);
+    const bool out_pinned = is_pinned(out->dist) && is_pinned(out->angle) && is_pinned(out->flags) && is_pinned(out->score) &&
+                            is_pinned(out->score_q32);
 
     Trace tr;
     HostCtx& hc = plan->host;
     std::lock_guard<std::mutex> lock(hc.mu);           // one host call per plan at a time
     HostSet (&set)[2] = hc.set;
-    DevBuf &ws = hc.ws, &occ = hc.occ, &sum = hc.sum, &sq = hc.sq, &box_all = hc.box_all, &rec_all = hc.rec_all;
+    DevBuf &ws = hc.ws, &occ = hc.occ, &sum = hc.sum, &sq = hc.sq, &box_all = hc.box_all, &rec_all = hc.rec_all, &wq = hc.wq;
     Stream &s_up = hc.s_up, &s_run = hc.s_run, &s_down = hc.s_down;
     typedef HostSet Set;
     CV_CUDA(s_up.create()); CV_CUDA(s_run.create()); CV_CUDA(s_down.create());
@@ -459,7 +481,8 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
         CV_CUDA(s.staged.alloc(hp.mode == CV_MODE_STAGED ? (size_t)TB * hp.staged_floats * 4 : 0));
         CV_CUDA(s.dist.alloc(out->dist ? (size_t)TB * P * 4 : 0));
         CV_CUDA(s.angle.alloc(out->angle ? (size_t)TB * A * 4 : 0));
-        CV_CUDA(s.flags.alloc(out->flags ? (size_t)TB * W * 4 : 0));
+        CV_CUDA(s.flags.alloc(need_flags ? (size_t)TB * W * 4 : 0));
+        CV_CUDA(s.wscore.alloc(want_ws ? (size_t)TB * 8 : 0));
         CV_CUDA(s.score.alloc(out->score ? (size_t)TB * 4 : 0));
         if (!in_pinned) {
             CV_CUDA(s.h_in.alloc((size_t)TB * frame_stride_floats * 4));
@@ -469,6 +492,7 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
             CV_CUDA(s.h_angle.alloc(out->angle ? (size_t)TB * A * 4 : 0));
             CV_CUDA(s.h_flags.alloc(out->flags ? (size_t)TB * W * 4 : 0));
             CV_CUDA(s.h_score.alloc(out->score ? (size_t)TB * 4 : 0));
+            CV_CUDA(s.h_wscore.alloc(want_ws ? (size_t)TB * 8 : 0));
         }
         CV_CUDA(s.uploaded.create()); CV_CUDA(s.computed.create()); CV_CUDA(s.downloaded.create());
     }
@@ -480,6 +504,10 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
     }
 
     tr.mark("features_host: buffers");
+    if (want_ws) {
+        CV_CUDA(wq.alloc((size_t)F * 8));
+        CV_CUDA(cudaMemcpyAsync(wq.p, out->weights_q32, (size_t)F * 8, cudaMemcpyHostToDevice, s_run.s));
+    }
     int64_t launches = 0;
     if (box_floats && n_frames > 0) {
         // boxes are tiny (<= 36 B per frame): upload and prepare all records once, outside the block loop
@@ -502,6 +530,7 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
             if (out->angle) parallel_memcpy(out->angle + pd.t0 * A, set[k].h_angle.p, (size_t)pd.n * A * 4);
             if (out->flags) memcpy(out->flags + pd.t0 * W, set[k].h_flags.p, (size_t)pd.n * W * 4);
             if (out->score) memcpy(out->score + pd.t0, set[k].h_score.p, (size_t)pd.n * 4);
+            if (want_ws) memcpy(out->score_q32 + pd.t0, set[k].h_wscore.p, (size_t)pd.n * 8);
         }
         pd.live = false;
         return CV_OK;
@@ -539,11 +568,16 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
             coords = s.staged.as<float>();
         }
         CvFrameOutputs fo{out->dist ? s.dist.as<float>() : nullptr, out->angle ? s.angle.as<float>() : nullptr,
-                          out->flags ? s.flags.as<uint32_t>() : nullptr, out->score ? s.score.as<int32_t>() : nullptr};
+                          need_flags ? s.flags.as<uint32_t>() : nullptr, out->score ? s.score.as<int32_t>() : nullptr};
         CvAggregates ag{occ.as<uint64_t>(), sum.as<double>(), sq.as<double>()};
         rc = caviar_run(plan, coords, frame_stride_floats, box_floats ? rec_all.as<float>() + t0 * kRecFloats : nullptr, n, &fo, want_agg ? &ag : nullptr, ws.p, s_run.s);
         if (rc != CV_OK) return rc;
         launches += g_launches;
+        if (want_ws) {
+            rc = caviar_weighted_scores(plan, s.flags.as<uint32_t>(), n, wq.as<int64_t>(), s.wscore.as<int64_t>(), s_run.s);
+            if (rc != CV_OK) return rc;
+            launches += g_launches;
+        }
         CV_CUDA(cudaEventRecord(s.computed.e, s_run.s));
         // download
         CV_CUDA(cudaStreamWaitEvent(s_down.s, s.computed.e, 0));
@@ -555,6 +589,8 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
         if (out->angle) CV_CUDA(cudaMemcpyAsync(adst, s.angle.p, (size_t)n * A * 4, cudaMemcpyDeviceToHost, s_down.s));
         if (out->flags) CV_CUDA(cudaMemcpyAsync(fdst, s.flags.p, (size_t)n * W * 4, cudaMemcpyDeviceToHost, s_down.s));
         if (out->score) CV_CUDA(cudaMemcpyAsync(sdst, s.score.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s_down.s));
+        if (want_ws) CV_CUDA(cudaMemcpyAsync(out_pinned ? out->score_q32 + t0 : s.h_wscore.as<int64_t>(), s.wscore.p, (size_t)n * 8,
+                                             cudaMemcpyDeviceToHost, s_down.s));
         CV_CUDA(cudaEventRecord(s.downloaded.e, s_down.s));
         pending[k] = Pending{t0, n, true};
         // the next upload into the other set may only start once that set's kernels are done: drain() above

@@ -67,6 +67,25 @@ def read_pairs(pairs: str, pairs_file: str) -> List[PairLabel]:
     return unique
 
 
+def read_tic_weights(path: str, labels: Sequence[PairLabel]) -> np.ndarray:
+    """Extension: the ``abs_loading`` CAVIAR writes next to every pair of its TIC file (``rank,pair,res1,res2,
+    abs_loading``, CAVIAR-1.0.py:141-147) as per-pair weights, in the order of ``labels``; pairs the file does not
+    weight get 0.  The first line of a label wins, like the column de-duplication."""
+    by_label = {}
+    with open(path, "r", encoding="utf-8", errors="ignore") as fh:
+        for line in fh:
+            hit = PairGrammar.many([line])
+            cells = line.strip().split(",")
+            if not hit or len(cells) < 2:
+                continue
+            try:
+                w = float(cells[-1])
+            except ValueError:
+                continue
+            by_label.setdefault(hit[0], w)
+    return np.array([by_label.get(lab, 0.0) for lab in labels], dtype=np.float64)
+
+
 def read_triplets(path: str) -> np.ndarray:
     """Extension: one ``a b c`` line of 1-based atom numbers per triplet (angle at b, distance a..c)."""
     rows = []
@@ -132,6 +151,9 @@ def build_parser() -> argparse.ArgumentParser:
     ap.add_argument("--hbond-cutoffs", type=float, nargs=2, default=(3.0, 135.0), metavar=("DIST", "ANGLE"))
     ap.add_argument("--npy-out", help="also save the (T, P) float32 matrix (fast binary side output)")
     ap.add_argument("--summary-out", help="JSON with per-pair occupancy / mean / variance and per-frame scores")
+    ap.add_argument("--weighted-score", action="store_true",
+                    help="--pairs-file is CAVIAR's TIC csv: weight every contact by its abs_loading in the per-frame score "
+                         "(written to --summary-out as frame_score_weighted)")
     ap.add_argument("--decimals", type=int, default=4)
     ap.add_argument("--frames-per-block", type=int, default=0)
     return ap
@@ -166,7 +188,12 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     block = args.frames_per_block or max(64, min(8192, (256 << 20) // max(1, 12 * len(used) + 4 * len(labels))))
     occ = np.zeros(len(labels) + len(triplets), dtype=np.uint64)
     s1 = np.zeros(len(occ)); s2 = np.zeros(len(occ))
-    scores = []
+    scores, wscores = [], []
+    weights = None
+    if args.weighted_score:
+        if not args.pairs_file:
+            sys.exit("[ERR] --weighted-score legge i pesi (abs_loading) da --pairs-file")
+        weights = np.concatenate([read_tic_weights(args.pairs_file, labels), np.zeros(len(triplets))])
     with FeaturePlan(len(used), pairs_c, trip_c if len(triplets) else None, box=box_kind, pair_cutoff=args.cutoff,
                      hbond_dist_cutoff=args.hbond_cutoffs[0], hbond_angle_cutoff=args.hbond_cutoffs[1]) as plan, \
             open(args.out, "wb") as fout:
@@ -176,12 +203,14 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
             lo, hi = int(ids[0]), int(ids[-1]) + 1
             xyz = traj.coords(lo, hi, stride)[:, used, :]
             cell = traj.cell(lo, hi, stride) if box_kind else None
-            res = plan.features_host(np.ascontiguousarray(xyz), cell, want=want)
+            res = plan.features_host(np.ascontiguousarray(xyz), cell, want=want, weights=weights)
             fout.write(format_rows(res["dist"], b0 + 1, 1, args.decimals))       # cpptraj's 1-based set index
             if npy is not None:
                 npy[b0:b0 + len(ids)] = res["dist"]
             occ += res["occupancy"]; s1 += res["sum"]; s2 += res["sumsq"]
             scores.append(res["score"])
+            if weights is not None:
+                wscores.append(res["score_weighted"])
     traj.close()
     if npy is not None:
         npy.flush()
@@ -193,7 +222,10 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
             json.dump({"frames": int(n_sel), "columns": colnames, "cutoff_A": args.cutoff,
                        "imaging": box_kind or "none", "occupancy": occ.tolist(), "mean": mean.tolist(),
                        "variance": var.tolist(),
-                       "frame_score": np.concatenate(scores).tolist() if scores else []}, fh)
+                       "frame_score": np.concatenate(scores).tolist() if scores else [],
+                       **({"pair_weights": weights[:len(labels)].tolist(),
+                           "frame_score_weighted": np.concatenate(wscores).tolist() if wscores else []}
+                          if weights is not None else {})}, fh)
     print(f"[DONE] Salvato CSV: {args.out}")
     print(f"[INFO] Colonne: {', '.join(colnames)}")
     return 0

@@ -270,10 +270,31 @@ class FeaturePlan:
         self.last_launches = int(_lib.lib.caviar_last_launch_count())
         return out
 
+    def weighted_scores(self, flags, weights):
+        """Per-frame weighted interaction score from the packed flags of ``run``: ``sum_f w[f] * flag[t, f]``.
+
+        ``weights``: (P + A,) array-like, pairs first then triplets -- e.g. the ``abs_loading`` column CAVIAR writes
+        next to each pair (CAVIAR-1.0.py:141-147).  They are rounded to 32.32 fixed point, summed exactly in int64
+        on the device (bit-reproducible, any summation order) and returned as a float64 CUDA tensor of shape (T,).
+        """
+        import torch
+        wq = quantize_weights(weights, self.F)
+        if flags.dtype not in (torch.int32, torch.uint32) or not flags.is_cuda or flags.dim() != 2 or flags.shape[1] != self.W \
+                or not flags.is_contiguous():
+            raise ValueError(f"flags must be the contiguous (T, {self.W}) int32 CUDA tensor written by run()")
+        wq_dev = torch.from_numpy(wq).to(flags.device)
+        out = torch.empty(flags.shape[0], dtype=torch.int64, device=flags.device)
+        check(_lib.lib.caviar_weighted_scores(self._handle, flags.data_ptr(), flags.shape[0], wq_dev.data_ptr(),
+                                              out.data_ptr(), self._stream_ptr()))
+        return out.to(torch.float64) / 4294967296.0
+
     # -- reference-facing host path ---------------------------------------------------------------
     def features_host(self, xyz: np.ndarray, box=None, want: Sequence[str] = ("dist", "angle", "flags", "score", "agg"),
-                      frames_per_block: int = 0, out: Optional[dict] = None) -> dict:
-        """HOST arrays in, HOST arrays out (H2D, kernels, D2H inside).  ``xyz`` is (T, N, 3) float32."""
+                      frames_per_block: int = 0, out: Optional[dict] = None, weights=None) -> dict:
+        """HOST arrays in, HOST arrays out (H2D, kernels, D2H inside).  ``xyz`` is (T, N, 3) float32.
+
+        ``weights`` (one per feature, pairs first) adds ``res["score_weighted"]``: float64 (T,), the per-frame sum of
+        the weights of the set flags (exact 32.32 fixed-point sum on the device, see ``weighted_scores``)."""
         xyz = np.asarray(xyz)
         if xyz.ndim != 3 or xyz.shape[1] != self.n_atoms or xyz.shape[2] != 3:
             raise ValueError(f"coordinates must be (T, {self.n_atoms}, 3), got {xyz.shape}")
@@ -294,6 +315,11 @@ class FeaturePlan:
             res["sum"] = np.zeros(self.F, dtype=np.float64)
             res["sumsq"] = np.zeros(self.F, dtype=np.float64)
         ho = CvHostOutputs()
+        wq = sq = None
+        if weights is not None:
+            wq = quantize_weights(weights, self.F)
+            sq = np.empty((T,), dtype=np.int64)
+            ho.weights_q32, ho.score_q32 = wq.ctypes.data, sq.ctypes.data
         for name in ("dist", "angle", "flags", "score", "occupancy", "sum", "sumsq"):
             arr = res.get(name)
             if arr is not None:
@@ -304,7 +330,19 @@ class FeaturePlan:
         check(_lib.lib.caviar_features_host(self._handle, xyz.ctypes.data, 3 * self.n_atoms,
                                             None if b is None else b.ctypes.data, T, C.byref(ho), int(frames_per_block)))
         self.last_launches = int(_lib.lib.caviar_last_launch_count())
+        if sq is not None:
+            res["score_weighted"] = sq.astype(np.float64) / 4294967296.0
         return res
+
+
+def quantize_weights(weights, n_features: int) -> np.ndarray:
+    """Weights -> 32.32 fixed point (int64), the form ``caviar_weighted_scores`` sums exactly.  |w| < 2^20."""
+    w = np.asarray(weights, dtype=np.float64).reshape(-1)
+    if w.shape[0] != n_features:
+        raise ValueError(f"need one weight per feature ({n_features}), got {w.shape[0]}")
+    if not np.isfinite(w).all() or np.abs(w).max(initial=0.0) >= 2.0 ** 20:
+        raise ValueError("weights must be finite and smaller than 2^20 in magnitude")
+    return np.rint(w * 4294967296.0).astype(np.int64)
 
 
 def unpack_flags(words: np.ndarray, n_pairs: int, n_triplets: int):

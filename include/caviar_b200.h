@@ -159,6 +159,14 @@ int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t frame_stride
 /* Number of kernels the last caviar_run / *_host call on this thread launched. */
 int64_t caviar_last_launch_count(void);
 
+/* Weighted frame scores from the packed flags of a run:  score[t] = sum over the set flags of frame t of
+ * weights_q32[f], f counting pairs first, then triplets (the weights CAVIAR publishes per pair
+ * are the abs_loading column of save_tic_csv, CAVIAR-1.0.py:141-147).  Weights and scores are 32.32 fixed point
+ * (int64 = value * 2^32, rounded by the caller), so the result is exact and independent of the summation order.
+ * flags_dev: [n_frames][n_flag_words] as written by caviar_run; all pointers are device pointers. */
+int caviar_weighted_scores(const CvPlan* plan, const uint32_t* flags_dev, int64_t n_frames,
+                           const int64_t* weights_q32_dev, int64_t* score_q32_dev, void* stream);
+
 /* Reference-facing, HOST buffers in and out (pageable or pinned).  Streams the
  * frames through pinned staging, double buffered.  Any output may be NULL.
  *   box_host: NULL | [T][3] | [T][9] float32 according to the plan's box_kind.
@@ -171,6 +179,8 @@ typedef struct CvHostOutputs {
     uint64_t* occupancy;  /* [P + A] */
     double*   sum;        /* [P + A] */
     double*   sumsq;      /* [P + A] */
+    const int64_t* weights_q32;  /* in, optional: [P + A] feature weights, 32.32 fixed point (see caviar_weighted_scores) */
+    int64_t*  score_q32;  /* [T] weighted frame scores, 32.32 fixed point; needs weights_q32 */
 } CvHostOutputs;
 
 int caviar_features_host(const CvPlan* plan, const float* xyz_host, int64_t frame_stride_floats,

@@ -407,6 +407,14 @@ def frame_scores(flags: np.ndarray) -> np.ndarray:
     return flags.sum(axis=1, dtype=np.int64).astype(np.int32)
 
 
+def weighted_frame_scores(flags: np.ndarray, weights) -> np.ndarray:
+    """Per-frame sum of the weights of the set flags, float64 (T,) (weights = e.g. the abs_loading
+    column of CAVIAR-1.0.py:141-147).  Weights are rounded to 32.32 fixed point and summed in int64: exact, and the
+    same number whatever the summation order -- the definition the device follows bit for bit."""
+    wq = np.rint(np.asarray(weights, dtype=np.float64) * 4294967296.0).astype(np.int64)
+    return (flags.astype(np.int64) @ wq).astype(np.float64) / 4294967296.0
+
+
 def pack_flags(flags: np.ndarray) -> np.ndarray:
     """(T, F) bool -> (T, ceil(F/32)) uint32; bit b of word w is feature 32*w + b."""
     t, f = flags.shape

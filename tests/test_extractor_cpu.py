@@ -164,3 +164,15 @@ def test_all_pairs_and_trim_mirror_the_reference(meta):
     class _Top:
         atom_names = ["N", "CA", "C", "O", "N", "H", "CA", "C"]
     assert ca_atom_indices(_Top()).tolist() == [1, 6]
+
+
+def test_tic_weights_follow_the_label_order(ext, tmp_path):
+    """abs_loading of CAVIAR's TIC csv (CAVIAR-1.0.py:141-147) as per-pair weights; unlisted pairs weigh 0."""
+    from oracle import caviar_oracle as orc
+    labels3 = {0: "ASP25", 1: "GLU216", 2: "ALA15", 3: "GLY26"}
+    rows = orc.tic_csv_rows([(0, 1), (2, 3)], np.array([-0.75, 0.125]), labels3)
+    f = tmp_path / "tic.csv"
+    f.write_text("\n".join(rows) + "\n")
+    labs = ext.read_pairs("SER1-THR2", str(f))
+    assert labs == [("SER", 1, "THR", 2), ("ASP", 25, "GLU", 216), ("ALA", 15, "GLY", 26)]
+    assert ext.read_tic_weights(str(f), labs).tolist() == [0.0, 0.75, 0.125]

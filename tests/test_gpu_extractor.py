@@ -53,7 +53,7 @@ def test_extractor_cli_against_oracle(tmp_path, capsys, box, stride):
     summ = tmp_path / "summary.json"
     rc = extractor.main(["--top", top, "--traj", nc, "--pairs-file", str(pf), "--pairs", f"{res_label[3]}-{res_label[40]}",
                          "--offset", str(offset), "--stride", str(stride), "--out", str(out),
-                         "--npy-out", str(npy), "--summary-out", str(summ)])
+                         "--npy-out", str(npy), "--summary-out", str(summ), "--weighted-score"])
     assert rc == 0
     printed = capsys.readouterr().out
     assert f"[DONE] Salvato CSV: {out}" in printed and "[INFO] Colonne:" in printed
@@ -85,6 +85,9 @@ def test_extractor_cli_against_oracle(tmp_path, capsys, box, stride):
     assert s["occupancy"] == (d.astype(np.float64) < 8.0).sum(0).tolist()
     np.testing.assert_allclose(s["mean"], d.astype(np.float64).mean(0), rtol=1e-12)
     assert s["frame_score"] == (d.astype(np.float64) < 8.0).sum(1).tolist()
+    # --weighted-score: abs_loading of the TIC file per column ((3,40) is listed there with |-0.4|)
+    assert s["pair_weights"] == [0.4, 0.5, 0.3, 0.2]
+    assert s["frame_score_weighted"] == orc.weighted_frame_scores(d.astype(np.float64) < 8.0, s["pair_weights"]).tolist()
 
 
 def test_extractor_error_paths(tmp_path):

@@ -251,3 +251,32 @@ def test_outputs_beyond_2_31_elements(cb):
         occ += (out.dist[t0:t0 + 512] < thr).sum(dim=0)
     assert torch.equal(occ, agg.occupancy)
     assert int(out.score.sum()) == int(occ.sum())
+
+
+@pytest.mark.parametrize("box", [None, "triclinic"])
+def test_weighted_frame_scores(cb, box):
+    """per-frame score weighted by CAVIAR's per-pair loadings -- exact fixed-point sums, bit for bit."""
+    import torch
+    from caviar_b200 import synthetic as syn
+    top = syn.make_topology(1 if box is None else 3, n_pairs=1500, n_triplets=333)
+    T = 41
+    x = syn.parity_frames(top, T, only_referenced=True)
+    pairs, trips = syn.compact_indices(top)
+    cell = syn.boxes_for(top, T)
+    rng = np.random.default_rng(6)
+    w = np.round(rng.random(len(pairs) + len(trips)) * 2.5, 6)              # abs_loading is printed with 6 decimals
+    with cb.FeaturePlan(x.shape[1], pairs, trips, box=top.cfg.box) as plan:
+        res = plan.features_host(x, cell, weights=w)
+        fp, ft = cb.unpack_flags(res["flags"], len(pairs), len(trips))
+        want = orc.weighted_frame_scores(np.concatenate([fp, ft], axis=1), w)
+        assert np.array_equal(res["score_weighted"], want)
+        res2 = plan.features_host(x, cell, want=("score",), weights=w, frames_per_block=7)     # flags not requested
+        assert np.array_equal(res2["score_weighted"], want) and "flags" not in res2
+        assert np.array_equal(plan.features_host(x, cell, want=("score",), weights=np.ones_like(w))["score_weighted"],
+                              res["score"].astype(np.float64))
+        xd = torch.from_numpy(x).cuda()
+        rec = plan.prepare_box(torch.from_numpy(cell).cuda()) if cell is not None else None
+        out = plan.run(plan.stage(xd, rec), rec)
+        assert np.array_equal(plan.weighted_scores(out.flags, w).cpu().numpy(), want)
+        with pytest.raises(ValueError):
+            plan.weighted_scores(out.flags, w[:-1])

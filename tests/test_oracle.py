@@ -203,3 +203,14 @@ def test_min_image_gap_flags_displacements_on_a_voronoi_face():
     assert np.isinf(orc.min_image_gap(d, None)).all()
     x = np.zeros((1, 3, 3)); x[0, 0] = (10.0, 0, 0); x[0, 2] = (0, 3.0, 0)
     assert orc.triplet_arm_gaps(x, [(0, 1, 2)], np.array([L, L, L]))[0, 0] == 0.0
+
+
+def test_weighted_frame_scores_are_exact_fixed_point_sums():
+    rng = np.random.default_rng(1)
+    flags = rng.random((7, 50)) < 0.4
+    w = rng.random(50) * 3
+    s = orc.weighted_frame_scores(flags, w)
+    np.testing.assert_allclose(s, flags @ w, rtol=0, atol=50 * 2.0 ** -33)
+    perm = rng.permutation(50)
+    assert np.array_equal(s, orc.weighted_frame_scores(flags[:, perm], w[perm]))       # order-independent, bit for bit
+    assert np.array_equal(orc.weighted_frame_scores(flags, np.ones(50)), orc.frame_scores(flags).astype(np.float64))
