@@ -703,6 +703,44 @@ extern "C" int caviar_pair_distances_host_f64(const double* xyz_host, int64_t n_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Host-side compaction of trajectory frames (the atom_slice of CAVIAR-1.0.py:335, at the file boundary)
+// ------------------------------------------------------------------------------------------------
+// out[t][k][:] = frame t of src, atom atoms[k], converted to native float32.  src is what a trajectory file maps
+// into memory: frames frame_stride_bytes apart, atoms as 3 x 4-byte floats, big-endian for Amber NetCDF (XDR).
+// Only the cache lines of the selected atoms are touched, frames are spread over the host threads: numpy needs a
+// byte-swapping copy of the WHOLE frame block plus a fancy-index pass (1.5 GB/s, 0.8 ms per 100k-atom frame each).
+extern "C" int caviar_compact_frames_host(const void* src, int64_t n_frames, int64_t frame_stride_bytes, int32_t n_atoms,
+                                          const int32_t* atoms, int64_t n_sel, int32_t big_endian, float* out) {
+    if (n_frames < 0 || n_sel < 0 || n_atoms <= 0) return fail(CV_E_INVALID, "bad shape");
+    if (n_frames == 0 || n_sel == 0) return CV_OK;
+    if (!src || !atoms || !out) return fail(CV_E_INVALID, "null argument");
+    if (frame_stride_bytes < 12ll * n_atoms) return fail(CV_E_INVALID, "frame stride smaller than 12*n_atoms bytes");
+    for (int64_t k = 0; k < n_sel; ++k)
+        if (atoms[k] < 0 || atoms[k] >= n_atoms) return fail(CV_E_INVALID, "atom index out of range");
+    unsigned hw = std::thread::hardware_concurrency();
+    const int64_t work = n_frames * n_sel;
+    int nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(hw ? hw : 4, 32), std::min<int64_t>(n_frames, work / 65536 + 1)));
+    auto run = [&](int k) {
+        const int64_t t0 = n_frames * k / nt, t1 = n_frames * (k + 1) / nt;
+        for (int64_t t = t0; t < t1; ++t) {
+            const unsigned char* frame = static_cast<const unsigned char*>(src) + t * frame_stride_bytes;
+            uint32_t* dst = reinterpret_cast<uint32_t*>(out + t * 3 * n_sel);
+            for (int64_t a = 0; a < n_sel; ++a) {
+                uint32_t v[3];
+                memcpy(v, frame + 12ll * atoms[a], 12);
+                if (big_endian) { v[0] = __builtin_bswap32(v[0]); v[1] = __builtin_bswap32(v[1]); v[2] = __builtin_bswap32(v[2]); }
+                dst[3 * a] = v[0]; dst[3 * a + 1] = v[1]; dst[3 * a + 2] = v[2];
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int k = 1; k < nt; ++k) pool.emplace_back(run, k);
+    run(0);
+    for (auto& th : pool) th.join();
+    return CV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // CSV rows (host): fixed-point formatting without printf
 // ------------------------------------------------------------------------------------------------
 namespace {

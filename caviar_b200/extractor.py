@@ -201,9 +201,9 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
         for b0 in range(0, n_sel, block):
             ids = frame_ids[b0:b0 + block]
             lo, hi = int(ids[0]), int(ids[-1]) + 1
-            xyz = traj.coords(lo, hi, stride)[:, used, :]
+            xyz = traj.coords_of(used, lo, hi, stride)          # native multi-threaded gather (+ byte order) from the mapped file
             cell = traj.cell(lo, hi, stride) if box_kind else None
-            res = plan.features_host(np.ascontiguousarray(xyz), cell, want=want, weights=weights)
+            res = plan.features_host(xyz, cell, want=want, weights=weights)
             fout.write(format_rows(res["dist"], b0 + 1, 1, args.decimals))       # cpptraj's 1-based set index
             if npy is not None:
                 npy[b0:b0 + len(ids)] = res["dist"]

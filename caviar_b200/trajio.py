@@ -15,6 +15,7 @@ when no NetCDF file is at hand.
 from __future__ import annotations
 
 import os
+import sys
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -205,6 +206,28 @@ class Trajectory:
 
     def coords(self, lo: int, hi: int, stride: int = 1) -> np.ndarray:
         return np.ascontiguousarray(self._xyz[lo:hi:stride], dtype=np.float32)
+
+    def coords_of(self, atoms: np.ndarray, lo: int, hi: int, stride: int = 1, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Frames ``lo:hi:stride`` of the selected atoms only, native float32 (n, len(atoms), 3): one multi-threaded
+        native pass over the memory-mapped file (byte order conversion included) instead of numpy's byte-swapping
+        copy of whole frames plus a fancy-index pass."""
+        from . import _lib
+        atoms = np.ascontiguousarray(atoms, dtype=np.int32)
+        stride = max(1, int(stride))
+        n = len(range(lo, hi, stride))
+        if out is None:
+            out = np.empty((n, len(atoms), 3), dtype=np.float32)
+        arr = self._xyz if isinstance(self._xyz, np.ndarray) else getattr(self._xyz, "data", None)
+        ok = (isinstance(arr, np.ndarray) and arr.ndim == 3 and arr.dtype.kind == "f" and arr.dtype.itemsize == 4
+              and arr.strides[2] == 4 and arr.strides[1] == 12 and arr.strides[0] >= 12 * self.n_atoms)
+        if not ok or n == 0 or len(atoms) == 0:                    # exotic layouts: numpy does it
+            out[...] = np.asarray(self._xyz[lo:hi:stride], dtype=np.float32)[:, atoms, :]
+            return out
+        big = arr.dtype.byteorder == ">" or (arr.dtype.byteorder == "=" and sys.byteorder == "big")
+        first = arr[lo:lo + 1]
+        _lib.check(_lib.lib.caviar_compact_frames_host(first.ctypes.data, n, arr.strides[0] * stride, self.n_atoms,
+                                                       atoms.ctypes.data, len(atoms), 1 if big else 0, out.ctypes.data))
+        return out
 
     def cell(self, lo: int, hi: int, stride: int = 1):
         kind = self.box_kind()

@@ -195,6 +195,13 @@ int caviar_pair_distances_host(const float* xyz_host, int64_t n_frames, int32_t 
                                const int32_t* pairs, int64_t n_pairs, float* dist_host);
 void caviar_release_cache(void);
 
+/* Host-side compaction at the trajectory-file boundary (the atom_slice of CAVIAR-1.0.py:335; what cpptraj's masks
+ * select at Extractor:133-138):  out[t][k] = atom atoms[k] of frame t, native float32 xyz.  `src` is the file's
+ * coordinate block as mapped into memory: frames frame_stride_bytes apart, 12 bytes per atom, big-endian when
+ * big_endian != 0 (Amber NetCDF is XDR).  Multi-threaded; touches only the selected atoms. */
+int caviar_compact_frames_host(const void* src, int64_t n_frames, int64_t frame_stride_bytes, int32_t n_atoms,
+                               const int32_t* atoms, int64_t n_sel, int32_t big_endian, float* out);
+
 /* Host-side CSV row formatter for the Extractor output (CAVIAR_Distances-Extractor.py:147-151,196-198: one frame
  * column, then one distance column per pair).  Formats rows x cols float32 values as
  *     "<first_index + r*index_step>,<v>,<v>,...\n"      with `decimals` fixed decimals (printf "%.Nf" rounding)

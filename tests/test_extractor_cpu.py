@@ -176,3 +176,29 @@ def test_tic_weights_follow_the_label_order(ext, tmp_path):
     labs = ext.read_pairs("SER1-THR2", str(f))
     assert labs == [("SER", 1, "THR", 2), ("ASP", 25, "GLU", 216), ("ALA", 15, "GLY", 26)]
     assert ext.read_tic_weights(str(f), labs).tolist() == [0.0, 0.75, 0.125]
+
+
+@pytest.mark.parametrize("fmt", ["nc", "npy"])
+def test_native_frame_compaction_equals_numpy(tmp_path, fmt):
+    """Trajectory.coords_of: selected atoms of strided frames straight from the mapped file (big-endian NetCDF records
+    or a native .npy), against numpy's byte-swapping copy + fancy index."""
+    from caviar_b200 import trajio
+    rng = np.random.default_rng(4)
+    T, N = 23, 157
+    xyz = rng.normal(0, 30, size=(T, N, 3)).astype(np.float32)
+    path = str(tmp_path / f"t.{fmt}")
+    if fmt == "nc":
+        trajio.write_netcdf(path, xyz, np.array([50.0, 60.0, 70.0]))
+    else:
+        np.save(path, xyz)
+    tr = trajio.Trajectory(path)
+    atoms = np.array([156, 0, 3, 3, 77, 12])
+    for lo, hi, stride in ((0, T, 1), (2, 21, 3), (5, 6, 1), (4, 4, 1)):
+        got = tr.coords_of(atoms, lo, hi, stride)
+        want = xyz[lo:hi:stride][:, atoms, :]
+        assert got.dtype == np.float32 and got.flags.c_contiguous and got.shape == want.shape
+        assert got.tobytes() == want.tobytes()
+    assert tr.coords_of(np.zeros(0, dtype=np.int64), 0, T).shape == (T, 0, 3)
+    with pytest.raises(Exception):
+        tr.coords_of(np.array([N]), 0, T)
+    tr.close()
