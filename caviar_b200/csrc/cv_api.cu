@@ -95,9 +95,13 @@ struct Event {
 // memcpy between pageable user memory and the pinned bounce buffers, spread over a few host threads: one core
 // moves ~10 GB/s, PCIe 5 x16 wants ~55 GB/s.
 void parallel_memcpy(void* dst, const void* src, size_t bytes) {
-    const size_t kMin = 8u << 20;
+    const size_t kMin = 4u << 20;
+    static const size_t kCopyThreads = [] {                // CAVIAR_COPY_THREADS overrides (A/B on the GPU box)
+        const char* e = std::getenv("CAVIAR_COPY_THREADS");
+        return (size_t)std::max(1, e ? atoi(e) : 16);
+    }();
     unsigned hw = std::thread::hardware_concurrency();
-    size_t nt = std::min<size_t>(std::min<size_t>(hw ? hw : 4, 8), bytes / kMin);
+    size_t nt = std::min<size_t>(std::min<size_t>(hw ? hw : 4, kCopyThreads), bytes / kMin);
     if (nt <= 1) { memcpy(dst, src, bytes); return; }
     std::vector<std::thread> pool;
     const size_t step = (bytes / nt + 4095) & ~(size_t)4095;
