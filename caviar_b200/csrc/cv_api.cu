@@ -294,9 +294,9 @@ extern "C" int caviar_plan_status(const CvPlan* plan, void* stream) {
 // ------------------------------------------------------------------------------------------------
 // the fused run
 // ------------------------------------------------------------------------------------------------
-template <int BOX, bool PIPE, bool FRAC>
+template <int BOX, bool PIPE, bool FRAC, bool LEAN>
 static cudaError_t launch_features(const CvPlan* plan, const RunParams& rp, cudaStream_t st) {
-    auto kern = features_kernel<BOX, PIPE, FRAC>;
+    auto kern = features_kernel<BOX, PIPE, FRAC, LEAN>;
     const int threads = PIPE ? kConsumerThreads + kProducerThreads : kConsumerThreads;
     const int smem = PIPE ? plan->hp.smem_bytes : 0;
     if (PIPE) {
@@ -325,7 +325,9 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
     if (!coords_dev) return fail(CV_E_INVALID, "null coordinate pointer");
     if (hp.desc.box_kind != CV_BOX_NONE && !boxrec_dev) return fail(CV_E_INVALID, "plan has a box but boxrec is null");
     const bool want_agg = agg && (agg->occupancy || agg->sum || agg->sumsq);
-    if (want_agg && !(agg->occupancy && agg->sum && agg->sumsq)) return fail(CV_E_INVALID, "aggregates are all-or-none");
+    const bool want_moments = want_agg && (agg->sum || agg->sumsq);
+    if (want_agg && !agg->occupancy) return fail(CV_E_INVALID, "aggregates: occupancy alone, or occupancy + sum + sumsq");
+    if (want_moments && !(agg->sum && agg->sumsq)) return fail(CV_E_INVALID, "aggregates: occupancy alone, or occupancy + sum + sumsq");
     if (!workspace_dev) return fail(CV_E_INVALID, "null workspace (CvPlanInfo.workspace_bytes of device memory)");
     cudaStream_t st = (cudaStream_t)stream;
 
@@ -379,12 +381,17 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
         rp.n_chunks = (int32_t)(n_big + n_small);
     }
     rp.queue = reinterpret_cast<unsigned int*>(workspace_dev);
+    // Lean run (a contact map: flags / scores / occupancy, no feature matrix, no moments): the kernel flavour that
+    // skips the moment accumulation and, without a box, the IEEE square root (flag decided on the squared distance).
+    const bool lean = !rp.dist && !rp.angle && !want_moments;
     if (want_agg) {
         rp.occ_part = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace_dev) + kQueueBytes);
-        rp.sum_part = reinterpret_cast<double*>(rp.occ_part + (long long)rp.n_chunks * F);
-        rp.sq_part = rp.sum_part + (long long)rp.n_chunks * F;
+        if (want_moments) {
+            rp.sum_part = reinterpret_cast<double*>(rp.occ_part + (long long)rp.n_chunks * F);
+            rp.sq_part = rp.sum_part + (long long)rp.n_chunks * F;
+        }
     }
-    rp.pair_thr = hp.pair_thr; rp.hb_dthr = hp.hb_dthr; rp.hb_athr = hp.hb_athr;
+    rp.pair_thr = hp.pair_thr; rp.pair_thr2 = hp.pair_thr2; rp.hb_dthr = hp.hb_dthr; rp.hb_athr = hp.hb_athr;
 
     CV_CUDA(cudaMemsetAsync(rp.queue, 0, sizeof(unsigned int), st));
     if (rp.score) CV_CUDA(cudaMemsetAsync(rp.score, 0, sizeof(int32_t) * n_frames, st));
@@ -394,17 +401,19 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
     // selection); staged periodic plans carry fixed-point triplet blocks
     const bool pipe = hp.mode != CV_MODE_DIRECT && !hp.gather_global;
     const bool frac = hp.mode == CV_MODE_STAGED && hp.desc.box_kind != CV_BOX_NONE;
+#define CV_LAUNCH(B, P_, F_) (lean ? launch_features<B, P_, F_, true>(plan, rp, st) : launch_features<B, P_, F_, false>(plan, rp, st))
     switch (hp.desc.box_kind * 4 + (pipe ? 2 : 0) + (frac ? 1 : 0)) {
-        case 0: e = launch_features<0, false, false>(plan, rp, st); break;
-        case 2: e = launch_features<0, true, false>(plan, rp, st); break;
-        case 4: e = launch_features<1, false, false>(plan, rp, st); break;
-        case 5: e = launch_features<1, false, true>(plan, rp, st); break;
-        case 7: e = launch_features<1, true, true>(plan, rp, st); break;
-        case 8: e = launch_features<2, false, false>(plan, rp, st); break;
-        case 9: e = launch_features<2, false, true>(plan, rp, st); break;
-        case 11: e = launch_features<2, true, true>(plan, rp, st); break;
+        case 0: e = CV_LAUNCH(0, false, false); break;
+        case 2: e = CV_LAUNCH(0, true, false); break;
+        case 4: e = CV_LAUNCH(1, false, false); break;
+        case 5: e = CV_LAUNCH(1, false, true); break;
+        case 7: e = CV_LAUNCH(1, true, true); break;
+        case 8: e = CV_LAUNCH(2, false, false); break;
+        case 9: e = CV_LAUNCH(2, false, true); break;
+        case 11: e = CV_LAUNCH(2, true, true); break;
         default: return fail(CV_E_INVALID, "internal: no kernel flavour for this plan");
     }
+#undef CV_LAUNCH
     if (e != cudaSuccess) return fail(CV_E_CUDA, std::string("features_kernel launch: ") + cudaGetErrorString(e));
     g_launches += 1;
     if (want_agg) {
@@ -456,7 +465,9 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
     if (box_kind != CV_BOX_NONE && n_frames > 0 && !box_host) return fail(CV_E_INVALID, "plan has a box but box_host is null");
     if (frame_stride_floats < 3ll * hp.desc.n_atoms) return fail(CV_E_INVALID, "frame stride smaller than 3*n_atoms");
     const bool want_agg = out->occupancy || out->sum || out->sumsq;
-    if (want_agg && !(out->occupancy && out->sum && out->sumsq)) return fail(CV_E_INVALID, "aggregates are all-or-none");
+    const bool want_moments = out->sum || out->sumsq;
+    if (want_agg && (!out->occupancy || (want_moments && !(out->sum && out->sumsq))))
+        return fail(CV_E_INVALID, "aggregates: occupancy alone, or occupancy + sum + sumsq");
     const bool want_ws = out->score_q32 != nullptr;
     if (want_ws && !out->weights_q32) return fail(CV_E_INVALID, "score_q32 needs weights_q32");
     const bool need_flags = out->flags || want_ws;          // the weighted scores are computed from the flag words
@@ -506,6 +517,8 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
         CV_CUDA(cudaMemsetAsync(sum.p, 0, (size_t)F * 8, s_run.s));
         CV_CUDA(cudaMemsetAsync(sq.p, 0, (size_t)F * 8, s_run.s));
     }
+    // occupancy alone + no feature matrix = a lean (contact-map) run, see caviar_run
+    const bool dev_moments = want_moments;
 
     tr.mark("features_host: buffers");
     if (want_ws) {
@@ -573,7 +586,7 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
         }
         CvFrameOutputs fo{out->dist ? s.dist.as<float>() : nullptr, out->angle ? s.angle.as<float>() : nullptr,
                           need_flags ? s.flags.as<uint32_t>() : nullptr, out->score ? s.score.as<int32_t>() : nullptr};
-        CvAggregates ag{occ.as<uint64_t>(), sum.as<double>(), sq.as<double>()};
+        CvAggregates ag{occ.as<uint64_t>(), dev_moments ? sum.as<double>() : nullptr, dev_moments ? sq.as<double>() : nullptr};
         rc = caviar_run(plan, coords, frame_stride_floats, box_floats ? rec_all.as<float>() + t0 * kRecFloats : nullptr, n, &fo, want_agg ? &ag : nullptr, ws.p, s_run.s);
         if (rc != CV_OK) return rc;
         launches += g_launches;
@@ -604,10 +617,11 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
     tr.mark("features_host: block loop");
     if (want_agg) {
         CV_CUDA(cudaStreamSynchronize(s_run.s));
-        if (n_frames == 0) { memset(out->occupancy, 0, F * 8); memset(out->sum, 0, F * 8); memset(out->sumsq, 0, F * 8); }
         CV_CUDA(cudaMemcpy(out->occupancy, occ.p, (size_t)F * 8, cudaMemcpyDeviceToHost));
-        CV_CUDA(cudaMemcpy(out->sum, sum.p, (size_t)F * 8, cudaMemcpyDeviceToHost));
-        CV_CUDA(cudaMemcpy(out->sumsq, sq.p, (size_t)F * 8, cudaMemcpyDeviceToHost));
+        if (want_moments) {
+            CV_CUDA(cudaMemcpy(out->sum, sum.p, (size_t)F * 8, cudaMemcpyDeviceToHost));
+            CV_CUDA(cudaMemcpy(out->sumsq, sq.p, (size_t)F * 8, cudaMemcpyDeviceToHost));
+        }
     }
     CV_CUDA(cudaStreamSynchronize(s_run.s));
     quiesce.armed = false;

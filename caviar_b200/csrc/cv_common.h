@@ -69,6 +69,7 @@ struct RunParams {
     double* sum_part;
     double* sq_part;
     float pair_thr;             // d < pair_thr
+    float pair_thr2;            // no box, lean runs: d*d-before-sqrt < pair_thr2  <=>  sqrt_rn(.) < pair_thr
     float hb_dthr;              // d(a,c) < hb_dthr
     float hb_athr;              // angle > hb_athr
     int32_t whole_frame;        // 1: a stage is frames_per_stage consecutive whole frames (one bulk copy)

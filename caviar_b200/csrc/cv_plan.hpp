@@ -36,7 +36,7 @@ struct HostPlan {
     int frames_per_stage = 1, n_stages = 0, stage_floats = 0, smem_bytes = 0, whole_frame = 0;
     int max_chunks = 1;                // upper bound of frame chunks per run (sizes the workspace)
     int64_t P = 0, A = 0, W = 0, Wp = 0;
-    float pair_thr = 0.f, hb_dthr = 0.f, hb_athr = 0.f;
+    float pair_thr = 0.f, pair_thr2 = 0.f, hb_dthr = 0.f, hb_athr = 0.f;
 };
 
 inline float f32_at_or_above(double c) {     // smallest float t with (double)t >= c:  (double)d < c  <=>  d < t
@@ -50,6 +50,16 @@ inline float f32_at_or_below(double c) {     // largest float t with (double)t <
     float t = (float)c;
     if ((double)t > c) t = std::nextafterf(t, -INFINITY);
     return t;
+}
+
+// smallest float s with sqrtf(s) >= t (sqrtf is correctly rounded and monotone):  s < result  <=>  sqrtf(s) < t
+inline float sq_threshold(float t) {
+    if (!(t > 0.f)) return 0.f;                       // sqrt(s) < t never holds for t <= 0 (or NaN): s < 0 never does
+    if (std::isinf(t)) return INFINITY;
+    float s = t * t;                                  // close; walk to the exact boundary
+    while (std::sqrt(s) >= t && s > 0.f) s = std::nextafterf(s, 0.f);
+    while (std::sqrt(s) < t) s = std::nextafterf(s, INFINITY);
+    return s;
 }
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -146,6 +156,7 @@ inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
     hp.Wp = (hp.P + 31) / 32;
     hp.W = hp.Wp + (hp.A + 31) / 32;
     hp.pair_thr = f32_at_or_above(d.pair_cutoff);
+    hp.pair_thr2 = sq_threshold(hp.pair_thr);
     hp.hb_dthr = f32_at_or_above(d.hbond_dist_cutoff);
     hp.hb_athr = f32_at_or_below(d.hbond_angle_cutoff);
     hp.n_sms = n_sms > 0 ? n_sms : 148;

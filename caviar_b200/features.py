@@ -210,8 +210,11 @@ class FeaturePlan:
         """Synchronise the current stream and raise if K0 met a NaN / Inf coordinate it had to stage as fixed point."""
         check(_lib.lib.caviar_plan_status(self._handle, self._stream_ptr()))
 
-    def new_aggregates(self, device="cuda") -> Aggregates:
+    def new_aggregates(self, device="cuda", moments: bool = True) -> Aggregates:
+        """Zeroed running aggregates; ``moments=False`` keeps the occupancy only (contact-map runs)."""
         import torch
+        if not moments:
+            return Aggregates(torch.zeros(self.F, dtype=torch.int64, device=device), None, None)
         return Aggregates(torch.zeros(self.F, dtype=torch.int64, device=device),
                           torch.zeros(self.F, dtype=torch.float64, device=device),
                           torch.zeros(self.F, dtype=torch.float64, device=device))
@@ -261,8 +264,10 @@ class FeaturePlan:
                 self._ws = self.new_workspace(coords.device)
             workspace = self._ws
         ws_ptr = workspace.data_ptr()
-        if aggregates is not None:
-            ag = CvAggregates(aggregates.occupancy.data_ptr(), aggregates.sum.data_ptr(), aggregates.sumsq.data_ptr())
+        if aggregates is not None:      # occupancy alone (sum = sumsq = None), or all three
+            ag = CvAggregates(aggregates.occupancy.data_ptr(),
+                              None if aggregates.sum is None else aggregates.sum.data_ptr(),
+                              None if aggregates.sumsq is None else aggregates.sumsq.data_ptr())
             ag_ptr = C.byref(ag)
         check(_lib.lib.caviar_run(self._handle, coords.data_ptr(), stride,
                                   None if boxrec is None else boxrec.data_ptr(), T,
@@ -314,6 +319,8 @@ class FeaturePlan:
             res["occupancy"] = np.zeros(self.F, dtype=np.uint64)
             res["sum"] = np.zeros(self.F, dtype=np.float64)
             res["sumsq"] = np.zeros(self.F, dtype=np.float64)
+        elif "occ" in want:                          # occupancy without the moments: with no dist / angle -> lean run
+            res["occupancy"] = np.zeros(self.F, dtype=np.uint64)
         ho = CvHostOutputs()
         wq = sq = None
         if weights is not None:

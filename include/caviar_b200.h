@@ -111,8 +111,11 @@ typedef struct CvFrameOutputs {
     int32_t*  score;   /* [n_frames] number of set flags in the frame */
 } CvFrameOutputs;
 
-/* Running per-feature aggregates (device pointers, all-or-none).  caviar_run ADDS
- * the block's totals, so a trajectory processed in several blocks accumulates. */
+/* Running per-feature aggregates (device pointers): occupancy alone, or occupancy + sum + sumsq.  caviar_run ADDS
+ * the block's totals, so a trajectory processed in several blocks accumulates.
+ * A run that asks for no dist / angle matrix and no moments -- a contact map: flags, scores, occupancy -- takes the
+ * lean kernel flavour (no moment accumulation; without a box the cut-off is applied to the squared distance,
+ * bit-identical flags, no square root). */
 typedef struct CvAggregates {
     uint64_t* occupancy;  /* [P + A] frames in which the flag was set */
     double*   sum;        /* [P + A] sum over frames of d (pairs) / angle (triplets) */

@@ -280,3 +280,37 @@ def test_weighted_frame_scores(cb, box):
         assert np.array_equal(plan.weighted_scores(out.flags, w).cpu().numpy(), want)
         with pytest.raises(ValueError):
             plan.weighted_scores(out.flags, w[:-1])
+
+
+@pytest.mark.parametrize("cfg_id,force", [(1, None), (1, "direct"), (2, None), (3, None), (3, "direct"), (4, None)])
+def test_lean_contact_map_runs_match_the_full_kernel(cb, cfg_id, force):
+    """Flags / scores / occupancy without a feature matrix and without moments take the lean kernel flavour (no box:
+    cut-off on the squared distance, no square root): every bit must equal the full run's."""
+    import torch
+    from caviar_b200 import synthetic as syn
+    top = syn.make_topology(cfg_id) if cfg_id != 3 else syn.make_topology(3, n_pairs=3000, n_triplets=700)
+    T = 24 if cfg_id == 4 else 150
+    x = syn.parity_frames(top, T, only_referenced=True)
+    pairs, trips = syn.compact_indices(top)
+    cell = syn.boxes_for(top, T)
+    with cb.FeaturePlan(x.shape[1], pairs, trips if len(trips) else None, box=top.cfg.box, force=force) as plan:
+        full = plan.features_host(x, cell)
+        lean = plan.features_host(x, cell, want=("flags", "score", "occ"), frames_per_block=37)
+        assert set(lean) == {"flags", "score", "occupancy"}
+        for k in ("flags", "score", "occupancy"):
+            assert np.array_equal(full[k], lean[k]), k
+        only_occ = plan.features_host(x, cell, want=("occ",))
+        assert np.array_equal(only_occ["occupancy"], full["occupancy"])
+        xd = torch.from_numpy(x).cuda()
+        rec = plan.prepare_box(torch.from_numpy(cell).cuda()) if cell is not None else None
+        agg = plan.new_aggregates(moments=False)
+        out = plan.run(plan.stage(xd, rec), rec, out=plan.alloc_outputs(T, want=("flags", "score")), aggregates=agg)
+        assert np.array_equal(out.flags.cpu().numpy().view(np.uint32), full["flags"])
+        assert np.array_equal(agg.occupancy.cpu().numpy().astype(np.uint64), full["occupancy"])
+    # thresholds that sit exactly on representable distances: the squared-distance compare must flip on the same bit
+    xk = np.zeros((1, 4, 3), np.float32); xk[0, 1] = (3, 4, 0); xk[0, 2] = (3, 4, 12); xk[0, 3] = (0.1, 0.2, 0.2)
+    for cut in (5.0, np.nextafter(np.float32(5.0), np.float32(6.0)), 13.0, 0.3, np.float32(0.3), 0.0, -1.0):
+        with cb.FeaturePlan(4, [(0, 1), (0, 2), (0, 3), (1, 1)], None, pair_cutoff=float(cut)) as plan:
+            a = plan.features_host(xk)
+            b = plan.features_host(xk, want=("flags", "score", "occ"))
+            assert np.array_equal(a["flags"], b["flags"]) and np.array_equal(a["occupancy"], b["occupancy"]), cut

@@ -122,7 +122,13 @@ def _check_features(cb, res, x, box, pairs, triplets, cuts, exact_dist=False):
         # within the distance tolerance: its direction -- and the angle -- is not defined at float32 resolution
         # (one such arm in 2e7 of the random-shape sweep).  Those are set aside, and there must be next to none.
         amb = orc.triplet_arm_gaps(x, triplets, box) < DIST_TOL
-        assert amb.mean() <= 1e-3
+        if amb.any():       # count ambiguous (frame, middle atom, end atom) arms once, however many triplets share them
+            tri = np.asarray(triplets, dtype=np.int64)
+            n_at = x.shape[1]
+            arms = set()
+            for t, k in np.argwhere(amb):
+                arms.add((t, tri[k, 1] * n_at + tri[k, 0])); arms.add((t, tri[k, 1] * n_at + tri[k, 2]))
+            assert len(arms) <= max(4, 2e-3 * T * A), f"{len(arms)} image-ambiguous arms"
         err = np.abs(res["angle"].astype(np.float64) - a64)
         assert err[~amb].max(initial=0.0) <= ANGLE_TOL, f"angle error {err[~amb].max():.3g} deg"
     fp, ft = cb.unpack_flags(res["flags"], P, A)

@@ -16,9 +16,10 @@ for force in (None, "staged"):
     plan = cb.FeaturePlan(U, pairs, None, box=top.cfg.box, force=force)
     coords = plan.stage(raw)
     for want, agg_on in ((("dist", "flags", "score"), True), (("flags", "score"), True), (("score",), True), ((), True),
-                         (("dist",), False), (("flags",), False), (("score",), False)):
+                         (("dist",), False), (("flags",), False), (("score",), False),
+                         (("flags", "score"), "occ"), ((), "occ")):       # "occ": occupancy without moments = lean run
         out = plan.alloc_outputs(T, want=want)
-        agg = plan.new_aggregates() if agg_on else None
+        agg = plan.new_aggregates(moments=agg_on != "occ") if agg_on else None
         for _ in range(2):
             plan.run(coords, None, out=out, aggregates=agg)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
