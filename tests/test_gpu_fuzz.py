@@ -58,6 +58,9 @@ def test_random_shapes_match_oracle(cb, seed):
                         hbond_dist_cutoff=cuts[1], hbond_angle_cutoff=cuts[2], force=force) as plan:
         res = plan.features_host(x, box, frames_per_block=int(rng.choice([0, 1, 5])))
         info = plan.info
+        lean = plan.features_host(x, box, want=("flags", "score", "occ"))          # contact-map flavour: same bits
+        for key in ("flags", "score", "occupancy"):
+            assert np.array_equal(lean[key], res[key]), f"lean run differs in {key}"
     if info["mode_name"] == "staged":
         assert info["gather_bank_conflicts"] >= 0
     if not P:
