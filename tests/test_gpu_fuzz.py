@@ -317,3 +317,36 @@ def test_lean_contact_map_runs_match_the_full_kernel(cb, cfg_id, force):
             a = plan.features_host(xk)
             b = plan.features_host(xk, want=("flags", "score", "occ"))
             assert np.array_equal(a["flags"], b["flags"]) and np.array_equal(a["occupancy"], b["occupancy"]), cut
+
+
+def test_downstream_pooled_mean_centring_and_covariance(cb):
+    """f3: the steps that follow the operator in CAVIAR-1.0.py (:342-343, :378-380, :396-401), on the device."""
+    import torch
+    from caviar_b200 import downstream as ds
+    rng = np.random.default_rng(12)
+    n, TA, TB = 40, 300, 260
+    pairs = orc.all_pairs(n, 5)
+    xa = (np.cumsum(rng.normal(0, 3.8, size=(n, 3)), 0)[None] + rng.normal(0, 0.6, size=(TA, n, 3))).astype(np.float32)
+    xb = (np.cumsum(rng.normal(0, 3.8, size=(n, 3)), 0)[None] + rng.normal(0, 0.6, size=(TB, n, 3))).astype(np.float32)
+    with cb.FeaturePlan(n, pairs, None) as plan:
+        da, db = torch.from_numpy(xa).cuda(), torch.from_numpy(xb).cuda()
+        agg_a, agg_b = plan.new_aggregates(), plan.new_aggregates()
+        out_a = plan.run(plan.stage(da), None, aggregates=agg_a)
+        out_b = plan.run(plan.stage(db), None, aggregates=agg_b)
+        mu = ds.pooled_mean(agg_a.sum, TA, agg_b.sum, TB)
+        XA, XB = ds.centred(out_a.dist, mu), ds.centred(out_b.dist, mu)
+        lag = 7
+        C00, Ctt, C0t = ds.cov_blocks(XA[:-lag], XA[lag:])
+        torch.cuda.synchronize()
+    # the reference's own lines, in numpy
+    distA, distB = orc.pair_distances(xa, pairs, n_jobs=1), orc.pair_distances(xb, pairs, n_jobs=1)
+    mu_ref = (distA.mean(axis=0) + distB.mean(axis=0)) / 2.0
+    np.testing.assert_allclose(mu.cpu().numpy(), mu_ref, rtol=1e-6)
+    XA_ref = distA - mu_ref
+    np.testing.assert_allclose(XA.cpu().numpy(), XA_ref, atol=5e-6)
+    np.testing.assert_allclose(XB.cpu().numpy(), distB - mu_ref, atol=5e-6)
+    X0, Xt = XA_ref[:-lag].astype(np.float64), XA_ref[lag:].astype(np.float64)
+    for got, want in ((C00, X0.T @ X0), (Ctt, Xt.T @ Xt), (C0t, X0.T @ Xt)):
+        np.testing.assert_allclose(got.cpu().numpy(), want / len(X0), rtol=2e-4, atol=2e-5)
+    with pytest.raises(TypeError):
+        ds.cov_blocks(XA_ref, XA_ref)                      # host arrays: refused, no CPU path
