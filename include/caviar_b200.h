@@ -20,11 +20,18 @@
  *                                mean over frames = sum/T), :539-545 (mean/var
  *                                from sum, sum of squares), :186 (threshold).
  *   caviar_stage_frames          CAVIAR-1.0.py:335-336,670  atom_slice(ca).xyz
- *                                (the compaction of selected atoms).
+ *                                (the compaction of selected atoms, on the device).
+ *   caviar_compact_frames_host   the same selection at the trajectory-file boundary
+ *                                (cpptraj's masks, Extractor:133-138), on the host.
+ *   caviar_weighted_scores       north_star extension: per-frame scores weighted by the
+ *                                abs_loading CAVIAR-1.0.py:141-147 publishes per pair.
+ *   caviar_format_csv            CAVIAR_Distances-Extractor.py:196-198 (CSV rows).
  *
  * Ownership: the caller owns every buffer it passes.  The library keeps no
  * pointer after a call returns, except inside the opaque CvPlan (device copies
- * of the index tables and cut-offs), which lives until caviar_plan_destroy().
+ * of the index tables and cut-offs), which lives until caviar_plan_destroy(),
+ * and the plan caviar_pair_distances_host keeps for its next call
+ * (caviar_release_cache() frees it).
  * A plan may be used from several streams at once as long as each stream has
  * its own workspace.
  */
