@@ -151,6 +151,32 @@ extern "C" int caviar_plan_describe(const CvPlanDesc* desc, int32_t n_sms, CvPla
     return CV_OK;
 }
 
+// Host-side planning only: the layout tables themselves, for tests that check the planner without a GPU.
+//   tile_desc : [n_tiles][8] int32 = {kind, f_begin, n_feat, idx_off, grp_off, grp_floats, fixed_point, 0}
+//   idx       : [3][n_tiles * 896] int32, float offset (3 * slot) of atom role 0 / 1 / 2 inside the tile's block
+//   src_off   : [staged_floats_per_frame] int32, staged float j <- float src_off[j] of the input frame
+// Pass NULL buffers to query the sizes (n_tiles via CvPlanInfo, src_off length = staged_floats_per_frame).
+extern "C" int caviar_plan_layout(const CvPlanDesc* desc, int32_t n_sms, int32_t* tile_desc, int32_t* idx, int32_t* src_off) {
+    if (!desc) return fail(CV_E_INVALID, "null argument");
+    HostPlan hp;
+    std::string why = build_plan(*desc, n_sms, hp);
+    if (!why.empty()) return fail(CV_E_INVALID, why);
+    const size_t C = hp.tiles.size();
+    if (tile_desc)
+        for (size_t c = 0; c < C; ++c) {
+            const TileDesc& t = hp.tiles[c];
+            const int32_t row[8] = {t.kind, t.f_begin, t.n_feat, t.idx_off, t.grp_off, t.grp_floats, t.reserved[0], 0};
+            memcpy(tile_desc + 8 * c, row, sizeof row);
+        }
+    if (idx) {
+        memcpy(idx, hp.idx0.data(), hp.idx0.size() * 4);
+        memcpy(idx + hp.idx0.size(), hp.idx1.data(), hp.idx1.size() * 4);
+        memcpy(idx + 2 * hp.idx0.size(), hp.idx2.data(), hp.idx2.size() * 4);
+    }
+    if (src_off && !hp.src_off.empty()) memcpy(src_off, hp.src_off.data(), hp.src_off.size() * 4);
+    return CV_OK;
+}
+
 template <typename T>
 static cudaError_t upload(T** dst, const std::vector<T>& src) {
     *dst = nullptr;

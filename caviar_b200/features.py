@@ -133,6 +133,7 @@ class FeaturePlan:
         desc.device = -1 if device is None else int(device)
         desc.n_ctas = int(n_ctas)
         info = CvPlanInfo()
+        self._desc, self._describe_sms = desc, describe_only_sms
         if describe_only_sms is not None:      # host-only dry run (no CUDA): used by CPU tests
             check(_lib.lib.caviar_plan_describe(C.byref(desc), int(describe_only_sms), C.byref(info)))
         else:
@@ -144,6 +145,17 @@ class FeaturePlan:
         self.W = int(info.n_flag_words)
         self.mode = int(info.mode)
         self.device = device
+
+    def layout(self) -> dict:
+        """The planner's tables (host-side, no CUDA): ``tiles`` (n_tiles, 8) = kind, f_begin, n_feat, idx_off, grp_off,
+        grp_floats, fixed_point, 0; ``idx`` (3, n_tiles*896) float offsets inside a tile's block; ``src_off`` (S,)."""
+        n_tiles, S = int(self.info["n_tiles"]), int(self.info["staged_floats_per_frame"])
+        tiles = np.zeros((n_tiles, 8), dtype=np.int32)
+        idx = np.zeros((3, n_tiles * 896), dtype=np.int32)
+        src = np.zeros(S, dtype=np.int32)
+        check(_lib.lib.caviar_plan_layout(C.byref(self._desc), int(self._describe_sms or 148), tiles.ctypes.data,
+                                          idx.ctypes.data, src.ctypes.data if S else None))
+        return {"tiles": tiles, "idx": idx, "src_off": src}
 
     # -- lifetime ---------------------------------------------------------------------------------
     def close(self):

@@ -132,6 +132,13 @@ typedef struct CvAggregates {
 /* Host-side planning only (no CUDA call): what plan_create would decide. */
 int caviar_plan_describe(const CvPlanDesc* desc, int32_t n_sms, CvPlanInfo* info);
 
+/* Host-side planning only: the layout tables a plan would upload, for CPU-side verification of the planner.
+ *   tile_desc [n_tiles][8] int32 = {kind, f_begin, n_feat, idx_off, grp_off, grp_floats, fixed_point, 0}
+ *   idx       [3][n_tiles*896] int32: float offset (3*slot) of atom role 0/1/2 inside the tile's block
+ *   src_off   [staged_floats_per_frame] int32: staged float j <- float src_off[j] of the input frame
+ * Any buffer may be NULL. */
+int caviar_plan_layout(const CvPlanDesc* desc, int32_t n_sms, int32_t* tile_desc, int32_t* idx, int32_t* src_off);
+
 int  caviar_plan_create(const CvPlanDesc* desc, CvPlan** plan);
 void caviar_plan_destroy(CvPlan* plan);
 int  caviar_plan_info(const CvPlan* plan, CvPlanInfo* info);

@@ -168,3 +168,58 @@ def test_large_overlapping_selections_do_not_blow_up_the_staged_layout(cb):
     assert info["staged_floats_per_frame"] <= 3 * (5000 + 304 + 8) and info["staged_fixedpoint_floats"] == 3 * 304
     info = cb.FeaturePlan(5000, pairs, None, box="ortho", describe_only_sms=148).info
     assert info["mode_name"] == "staged" and info["staged_floats_per_frame"] <= 3 * 5004     # periodic: compact frame via K0
+
+
+def _check_layout(cb, n, pairs, trips, box, force=None):
+    """Every feature slot of every tile must resolve, through the index tables and the staged layout, to the atoms
+    the caller's list names -- whatever the planner decided (per-tile blocks in bank order, shared block, compact
+    per-kind blocks, zero-copy, direct)."""
+    plan = cb.FeaturePlan(n, pairs, trips, box=box, force=force, describe_only_sms=148)
+    lay, info = plan.layout(), plan.info
+    staged = info["mode_name"] == "staged"
+    src = lay["src_off"]
+    if staged:
+        assert len(src) % 12 == 0 and (src.reshape(-1, 3) % 3 == [0, 1, 2]).all()
+        assert (np.diff(src.reshape(-1, 3), axis=1) == 1).all() and src.min() >= 0 and src.max() < 3 * n
+    P = 0 if pairs is None else len(pairs)
+    seen_pairs = seen_trips = 0
+    for kind, f_begin, n_feat, idx_off, grp_off, grp_floats, fixed, _ in lay["tiles"]:
+        want = (np.asarray(pairs)[f_begin:f_begin + n_feat] if kind == 0 else np.asarray(trips)[f_begin:f_begin + n_feat])
+        for role in range(want.shape[1]):
+            off = lay["idx"][role, idx_off:idx_off + n_feat]
+            assert (off % 3 == 0).all() and off.min() >= 0
+            if staged:
+                assert off.max() + 2 < grp_floats and grp_off + grp_floats <= len(src)
+                atoms = src[grp_off + off] // 3
+            else:
+                atoms = off // 3
+            assert np.array_equal(atoms, want[:, role]), (kind, f_begin, role)
+        if staged and box is not None and kind == 1:
+            assert fixed == 1 and grp_off >= len(src) - info["staged_fixedpoint_floats"]
+        seen_pairs += n_feat if kind == 0 else 0
+        seen_trips += n_feat if kind == 1 else 0
+    assert seen_pairs == P and seen_trips == (0 if trips is None else len(trips))
+    return info
+
+
+def test_planner_layout_resolves_every_feature_to_its_atoms(cb):
+    rng = np.random.default_rng(21)
+    # random lists: per-tile blocks in bank-conflict-free order, with and without a box / triplets
+    n = 5000
+    pairs, trips = rng.integers(0, n, size=(3001, 2)), rng.integers(0, n, size=(1234, 3))
+    for box in (None, "ortho", "triclinic"):
+        info = _check_layout(cb, n, pairs, trips, box)
+        assert info["mode_name"] == "staged" and info["stages"] > 0
+    _check_layout(cb, n, pairs, None, "ortho", force="direct")
+    # heavy sharing over few atoms: holes in the bank order, shared block, zero-copy
+    few = rng.integers(0, 60, size=(5000, 2))
+    assert _check_layout(cb, 60, few, None, None)["mode_name"] == "zerocopy"
+    assert _check_layout(cb, 61, few, None, None)["mode_name"] == "staged"
+    _check_layout(cb, 60, few, rng.integers(0, 60, size=(300, 3)), "triclinic")
+    _check_layout(cb, 60, few, None, None, force="staged")
+    # large overlapping selection of a periodic plan: compact per-kind blocks gathered from global memory
+    rows = np.repeat(np.arange(0, 3000, 50), 3000)
+    big = np.stack([rows, np.tile(np.arange(3000), 60)], 1)
+    info = _check_layout(cb, 3000, big, rng.integers(0, 3000, size=(100, 3)), "ortho")
+    assert info["mode_name"] == "staged" and info["stages"] == 0
+    assert _check_layout(cb, 3000, big, None, None)["mode_name"] == "direct"
