@@ -88,3 +88,22 @@ def test_planner_invariants(n_atoms, n_pairs, n_trip, seed, box, force):
         assert s % 12 == 0 and s >= 3 * len(used) and s <= 3 * (2 * n_pairs + 3 * n_trip) + 12 * info["n_tiles"]
     if info["mode_name"] == "zerocopy":
         assert force is None and n_atoms % 4 == 0 and n_atoms * 12 <= 48 * 1024
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(0, 2 ** 31 - 1), st.sampled_from([None, "ortho", "triclinic"]), st.sampled_from([None, "staged", "direct"]))
+def test_planner_layout_property(seed, box, force):
+    """Whatever the list looks like (sizes, sharing, degenerate features), every feature slot of the plan resolves to
+    the caller's atoms -- checked through caviar_plan_layout, no GPU involved."""
+    import caviar_b200 as cb
+    from test_abi_cpu import _check_layout
+    rng = np.random.default_rng(seed)
+    n = int(rng.choice([1, 2, 5, 33, 64, 300, 2048, 5000]))
+    hot = max(1, n // int(rng.choice([1, 3, 40])))
+    P = int(rng.choice([0, 1, 32, 897, 1793, 4000]))
+    A = int(rng.choice([0, 1, 225, 673, 1500]))
+    if P + A == 0:
+        P = 3
+    pairs = rng.integers(0, hot, size=(P, 2)) if P else None
+    trips = rng.integers(0, hot, size=(A, 3)) if A else None
+    _check_layout(cb, n, pairs, trips, box, force=force)
