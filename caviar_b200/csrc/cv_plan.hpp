@@ -1,9 +1,11 @@
 // Host-side planning for the CAVIAR pair-feature path (pure C++, no CUDA calls).
 //
 // A plan cuts the feature list (pairs first, then triplets; column order = input order, CAVIAR-1.0.py:122)
-// into column tiles of <= 896 features, decides how coordinates reach the SMs (direct gather / zero-copy TMA /
-// staged TMA), lays out the staged coordinate blocks, and assigns every persistent CTA one tile and a frame
-// partition so that pair indices stay in registers for the lifetime of the CTA.
+// into column tiles of <= 896 features, decides how coordinates reach the SMs (per-tile staged blocks streamed by
+// TMA / one shared block or the caller's frame streamed whole / gathers from global memory for large overlapping
+// selections), lays out the staged blocks (bank-conflict-free atom order, fixed-point blocks of periodic triplet
+// tiles) and sizes the TMA ring and the work queue.  (tile, frame chunk) work items are handed to the persistent
+// CTAs at run time, so that the atom offsets of a tile stay in registers for a whole item.
 #pragma once
 #include <algorithm>
 #include <cmath>
