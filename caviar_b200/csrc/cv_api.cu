@@ -326,8 +326,14 @@ static cudaError_t launch_features(const CvPlan* plan, const RunParams& rp, cuda
     const int threads = PIPE ? kConsumerThreads + kProducerThreads : kConsumerThreads;
     const int smem = PIPE ? plan->hp.smem_bytes : 0;
     if (PIPE) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
+        // opt in to > 48 KB of dynamic shared memory once per kernel flavour and device (grow-only, benign race)
+        static int granted[64] = {0};
+        const int dev = plan->device & 63;
+        if (smem > granted[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+            granted[dev] = smem;
+        }
     }
     kern<<<plan->hp.n_ctas, threads, smem, st>>>(rp);
     return cudaGetLastError();
@@ -444,8 +450,14 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
     g_launches += 1;
     if (want_agg) {
         const unsigned blocks = (unsigned)((F + 31) / 32);
-        finalize_kernel<<<blocks, dim3(32, kFinalizeSlices), 0, st>>>(rp.occ_part, rp.sum_part, rp.sq_part, F, rp.n_chunks,
-                                                reinterpret_cast<unsigned long long*>(agg->occupancy), agg->sum, agg->sumsq);
+        unsigned long long* occ_out = reinterpret_cast<unsigned long long*>(agg->occupancy);
+        const bool many = rp.n_chunks >= kFinalizeManyRows;      // (a function of the run's shape only: reproducible)
+#define CV_FINALIZE(M, S)                                                                                          \
+        finalize_kernel<M, S><<<blocks, dim3(32, S), 0, st>>>(rp.occ_part, rp.sum_part, rp.sq_part, F, rp.n_chunks, \
+                                                              occ_out, agg->sum, agg->sumsq)
+        if (want_moments) { if (many) CV_FINALIZE(true, kFinalizeSlicesMany); else CV_FINALIZE(true, kFinalizeSlicesFew); }
+        else              { if (many) CV_FINALIZE(false, kFinalizeSlicesMany); else CV_FINALIZE(false, kFinalizeSlicesFew); }
+#undef CV_FINALIZE
         CV_CUDA(cudaGetLastError());
         g_launches += 1;
     }

@@ -78,7 +78,8 @@ struct RunParams {
 constexpr int kQueueBytes = 256;        // the work counter lives at the head of the caller's workspace
 constexpr int kMinChunkFrames = 32;     // ... but never fewer frames per item than this (short blocks of the host path)
 constexpr int kMinTailFrames = 8;       // ... except the quarter-size items of the tail (per-item flush = 24 B per feature)
-constexpr int kFinalizeSlices = 8;      // chunk slices summed in parallel, then combined in a fixed order
+constexpr int kFinalizeSlicesFew = 8, kFinalizeSlicesMany = 32;   // chunk slices summed in parallel, combined in a fixed order
+constexpr int kFinalizeManyRows = 128;   // from this many chunk rows on, the 32-slice shape
 constexpr int kItemsPerCta = 32;        // work items per CTA the chunking aims for (tail imbalance <= ~1/16)
 
 }  // namespace cv
