@@ -223,3 +223,25 @@ def test_planner_layout_resolves_every_feature_to_its_atoms(cb):
     info = _check_layout(cb, 3000, big, rng.integers(0, 3000, size=(100, 3)), "ortho")
     assert info["mode_name"] == "staged" and info["stages"] == 0
     assert _check_layout(cb, 3000, big, None, None)["mode_name"] == "direct"
+
+
+def test_plain_c_host_links_against_the_abi(cb, tmp_path):
+    """examples/pair_distances.c: a C program binds the same header and library (no Python below the ABI).  Without a
+    GPU the library refuses loudly (CV_E_NO_DEVICE) -- there is no CPU fallback to fall into."""
+    import shutil
+    import subprocess
+    import torch
+    from caviar_b200.build import LIB_PATH
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "pair_distances")
+    libdir = os.path.dirname(LIB_PATH)
+    subprocess.run([gcc, "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "pair_distances.c"),
+                    "-o", exe, "-L", libdir, "-lcaviar_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    res = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert "ABI version 2" in res.stdout
+    if torch.cuda.is_available():
+        assert res.returncode == 0 and "frame 1: 5.0000 20.0000 5.0000" in res.stdout
+    else:
+        assert res.returncode == 2 and "no CPU fallback" in res.stdout
