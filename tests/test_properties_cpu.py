@@ -107,3 +107,34 @@ def test_planner_layout_property(seed, box, force):
     pairs = rng.integers(0, hot, size=(P, 2)) if P else None
     trips = rng.integers(0, hot, size=(A, 3)) if A else None
     _check_layout(cb, n, pairs, trips, box, force=force)
+
+
+@settings(max_examples=40, deadline=None)
+@given(systems(), st.sampled_from(["none", "ortho", "triclinic"]))
+def test_c_oracle_agrees_with_numpy_oracle_property(sysm, kind):
+    """The two independent restatements (numpy, C) agree on random cells and lists: distances to 1e-9 A, angles to
+    1e-5 deg (acos noise at 0 / 180), the fused C pass with the flag / score / occupancy definitions."""
+    from oracle import c_oracle as co
+    x, h1, pairs, trips, rng = sysm
+    x = x.astype(np.float32)
+    T = x.shape[0]
+    if kind == "none":
+        box = None
+    elif kind == "ortho":
+        box = np.broadcast_to(np.diag(h1), (T, 3)).copy()
+    else:
+        box = np.broadcast_to(h1, (T, 3, 3)).copy()
+    d_np, d_c = orc.pbc_pair_distances(x, pairs, box), co.pbc_pair_distances(x, pairs, box, n_threads=2)
+    np.testing.assert_allclose(d_c, d_np, rtol=0, atol=1e-9)
+    gap = orc.triplet_arm_gaps(x, trips, box)
+    a_np = orc.triplet_angles(x, trips, box)
+    a_c, e_c = co.triplet_angles(x, trips, box, n_threads=2, with_end_distances=True)
+    ok = gap > 1e-6                                      # an arm on a Voronoi face may legitimately pick either image
+    np.testing.assert_allclose(a_c[ok], a_np[ok], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(e_c, orc.triplet_end_distances(x, trips, box), rtol=0, atol=1e-9)
+    cuts = (9.0, 8.0, 70.0)
+    f = co.fused_pass(x, pairs, trips, box, *cuts, n_threads=3)
+    flags = np.concatenate([orc.contact_flags(f["dist"], cuts[0]),
+                            orc.hbond_flags(e_c.astype(np.float32), f["angle"], cuts[1], cuts[2])], axis=1)
+    assert np.array_equal(f["flags"].astype(bool), flags)
+    assert np.array_equal(f["score"], orc.frame_scores(flags)) and np.array_equal(f["occupancy"], orc.occupancy(flags))
