@@ -86,6 +86,8 @@ SYMBOLS = {
     "caviar_pair_distances_host_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "caviar_compact_frames_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int32,
                                            C.c_void_p]),
+    "caviar_compact_frames_soa_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64,
+                                               C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "caviar_format_csv": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                       C.c_void_p, C.c_int64]),
     "caviar_last_error": (C.c_char_p, []),

@@ -796,6 +796,44 @@ extern "C" int caviar_compact_frames_host(const void* src, int64_t n_frames, int
     return CV_OK;
 }
 
+// The same for trajectory formats that keep a frame as three separate coordinate arrays (DCD: X[N], Y[N], Z[N], each a
+// Fortran record): x_off / y_off / z_off are the byte offsets of those arrays inside a frame.
+extern "C" int caviar_compact_frames_soa_host(const void* src, int64_t n_frames, int64_t frame_stride_bytes, int32_t n_atoms,
+                                              int64_t x_off, int64_t y_off, int64_t z_off, const int32_t* atoms,
+                                              int64_t n_sel, int32_t byte_swap, float* out) {
+    if (n_frames < 0 || n_sel < 0 || n_atoms <= 0 || x_off < 0 || y_off < 0 || z_off < 0) return fail(CV_E_INVALID, "bad shape");
+    if (n_frames == 0 || n_sel == 0) return CV_OK;
+    if (!src || !atoms || !out) return fail(CV_E_INVALID, "null argument");
+    const int64_t last = std::max(x_off, std::max(y_off, z_off)) + 4ll * n_atoms;
+    if (frame_stride_bytes < last) return fail(CV_E_INVALID, "frame stride smaller than the coordinate arrays");
+    for (int64_t k = 0; k < n_sel; ++k)
+        if (atoms[k] < 0 || atoms[k] >= n_atoms) return fail(CV_E_INVALID, "atom index out of range");
+    unsigned hw = std::thread::hardware_concurrency();
+    const int64_t work = n_frames * n_sel;
+    int nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(hw ? hw : 4, 32), std::min<int64_t>(n_frames, work / 65536 + 1)));
+    auto run = [&](int k) {
+        const int64_t t0 = n_frames * k / nt, t1 = n_frames * (k + 1) / nt;
+        const int64_t off[3] = {x_off, y_off, z_off};
+        for (int64_t t = t0; t < t1; ++t) {
+            const unsigned char* frame = static_cast<const unsigned char*>(src) + t * frame_stride_bytes;
+            uint32_t* dst = reinterpret_cast<uint32_t*>(out + t * 3 * n_sel);
+            for (int c = 0; c < 3; ++c) {
+                const unsigned char* arr = frame + off[c];
+                for (int64_t a = 0; a < n_sel; ++a) {
+                    uint32_t v;
+                    memcpy(&v, arr + 4ll * atoms[a], 4);
+                    dst[3 * a + c] = byte_swap ? __builtin_bswap32(v) : v;
+                }
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int k = 1; k < nt; ++k) pool.emplace_back(run, k);
+    run(0);
+    for (auto& th : pool) th.join();
+    return CV_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // CSV rows (host): fixed-point formatting without printf
 // ------------------------------------------------------------------------------------------------

@@ -9,6 +9,10 @@ Here the two formats that workflow uses are read directly:
 * Amber prmtop topologies (``%FLAG ATOM_NAME / RESIDUE_LABEL / RESIDUE_POINTER``) and PDB files, only as far as
   the ``:{idx}@CA`` / ``resid {n}@CA`` selections of the reference need (Extractor:127-138).
 
+* CHARMM / NAMD DCD trajectories (``.dcd``): Fortran-record file, per frame an optional unit-cell record (6 doubles)
+  and three float32 arrays X[N], Y[N], Z[N]; either byte order; memory-mapped, the selected atoms are gathered
+  natively.  Files with fixed atoms (NAMNF > 0) or 4-D coordinates are refused.
+
 A ``.npy`` array ``(T, N, 3)`` is accepted as a trajectory too (no box), which is what the tests and benchmarks use
 when no NetCDF file is at hand.
 """
@@ -177,6 +181,13 @@ class Trajectory:
         self.path = path
         ext = os.path.splitext(path)[1].lower()
         self._nc = None
+        self._dcd = None
+        if ext == ".dcd":
+            self._dcd = _DcdFile(path)
+            self._xyz = None
+            self._len = self._ang = None
+            self.n_frames, self.n_atoms = self._dcd.n_frames, self._dcd.n_atoms
+            return
         if ext == ".npy":
             self._xyz = np.load(path, mmap_mode="r")
             if self._xyz.ndim != 3 or self._xyz.shape[2] != 3:
@@ -194,6 +205,8 @@ class Trajectory:
 
     @property
     def has_box(self) -> bool:
+        if self._dcd is not None:
+            return self._dcd.has_cell and self.n_frames > 0 and bool(np.all(self._dcd.cell(0, 1)[0][0] > 0))
         if self._len is None or self._ang is None or self.n_frames == 0:
             return False
         return bool(np.all(np.asarray(self._len[0]) > 0))
@@ -201,10 +214,12 @@ class Trajectory:
     def box_kind(self) -> Optional[str]:
         if not self.has_box:
             return None
-        ang = np.asarray(self._ang[0], dtype=np.float64)
+        ang = self._dcd.cell(0, 1)[1][0] if self._dcd is not None else np.asarray(self._ang[0], dtype=np.float64)
         return "ortho" if np.allclose(ang, 90.0, atol=1e-6) else "triclinic"
 
     def coords(self, lo: int, hi: int, stride: int = 1) -> np.ndarray:
+        if self._dcd is not None:
+            return self.coords_of(np.arange(self.n_atoms), lo, hi, stride)
         return np.ascontiguousarray(self._xyz[lo:hi:stride], dtype=np.float32)
 
     def coords_of(self, atoms: np.ndarray, lo: int, hi: int, stride: int = 1, out: Optional[np.ndarray] = None) -> np.ndarray:
@@ -217,6 +232,13 @@ class Trajectory:
         n = len(range(lo, hi, stride))
         if out is None:
             out = np.empty((n, len(atoms), 3), dtype=np.float32)
+        if self._dcd is not None:
+            if n and len(atoms):
+                d = self._dcd
+                _lib.check(_lib.lib.caviar_compact_frames_soa_host(
+                    d.frame_ptr(lo), n, d.frame_bytes * stride, d.n_atoms, d.x_off, d.y_off, d.z_off,
+                    atoms.ctypes.data, len(atoms), 1 if d.swap else 0, out.ctypes.data))
+            return out
         arr = self._xyz if isinstance(self._xyz, np.ndarray) else getattr(self._xyz, "data", None)
         ok = (isinstance(arr, np.ndarray) and arr.ndim == 3 and arr.dtype.kind == "f" and arr.dtype.itemsize == 4
               and arr.strides[2] == 4 and arr.strides[1] == 12 and arr.strides[0] >= 12 * self.n_atoms)
@@ -233,12 +255,19 @@ class Trajectory:
         kind = self.box_kind()
         if kind is None:
             return None
-        L = np.asarray(self._len[lo:hi:stride], dtype=np.float64)
+        if self._dcd is not None:
+            L, A = self._dcd.cell(lo, hi, stride)
+        else:
+            L = np.asarray(self._len[lo:hi:stride], dtype=np.float64)
+            A = np.asarray(self._ang[lo:hi:stride], dtype=np.float64)
         if kind == "ortho":
             return L.astype(np.float32)
-        return cell_to_matrix(L, np.asarray(self._ang[lo:hi:stride], dtype=np.float64)).astype(np.float32)
+        return cell_to_matrix(L, A).astype(np.float32)
 
     def close(self):
+        if self._dcd is not None:
+            self._dcd.close()
+            self._dcd = None
         if self._nc is not None:
             self._xyz = self._len = self._ang = None
             try:
@@ -246,6 +275,93 @@ class Trajectory:
             except Exception:
                 pass
             self._nc = None
+
+
+class _DcdFile:
+    """Layout of a CHARMM / NAMD DCD file over a read-only memory map (no frame is copied here)."""
+
+    def __init__(self, path: str):
+        self._mm = np.memmap(path, dtype=np.uint8, mode="r")
+        mm = self._mm
+        if mm.size < 100:
+            raise ValueError(f"{path}: too short for a DCD file")
+        first = int(mm[:4].view("<i4")[0])
+        if first == 84:
+            self.swap, e = sys.byteorder != "little", "<"
+        elif int(mm[:4].view(">i4")[0]) == 84:
+            self.swap, e = sys.byteorder != "big", ">"
+        else:
+            raise ValueError(f"{path}: not a DCD file (first record marker is not 84)")
+        if bytes(mm[4:8]) != b"CORD":
+            raise ValueError(f"{path}: DCD header without the CORD tag")
+        icntrl = mm[8:88].view(e + "i4")
+        n_set, namnf, has_cell, four_d = int(icntrl[0]), int(icntrl[8]), int(icntrl[10]), int(icntrl[11])
+        if namnf != 0 or four_d != 0:
+            raise ValueError(f"{path}: DCD files with fixed atoms or 4-D coordinates are not supported")
+        pos = 92
+        title = int(mm[pos:pos + 4].view(e + "i4")[0])
+        pos += 4 + title + 4
+        if int(mm[pos:pos + 4].view(e + "i4")[0]) != 4:
+            raise ValueError(f"{path}: malformed atom-count record")
+        self.n_atoms = int(mm[pos + 4:pos + 8].view(e + "i4")[0])
+        pos += 12
+        self.has_cell = bool(has_cell)
+        self.first_frame = pos
+        cell_b = 56 if self.has_cell else 0                     # 4 + 6 doubles + 4
+        arr_b = 4 * self.n_atoms + 8                            # marker + N floats + marker
+        self.frame_bytes = cell_b + 3 * arr_b
+        self.x_off, self.y_off, self.z_off = cell_b + 4, cell_b + arr_b + 4, cell_b + 2 * arr_b + 4
+        avail = (mm.size - pos) // self.frame_bytes if self.frame_bytes else 0
+        self.n_frames = min(n_set, avail) if n_set > 0 else avail      # some writers leave NSET at 0
+        self._e = e
+
+    def frame_ptr(self, t: int) -> int:
+        return self._mm.ctypes.data + self.first_frame + t * self.frame_bytes
+
+    def cell(self, lo: int, hi: int, stride: int = 1):
+        """(lengths (n,3), angles_deg (n,3)) from the per-frame record A, gamma, B, beta, alpha, C (CHARMM stores the
+        cosines of the angles, NAMD and others degrees)."""
+        idx = np.arange(lo, hi, max(1, stride))
+        raw = np.empty((len(idx), 6), dtype=np.float64)
+        for k, t in enumerate(idx):
+            o = self.first_frame + int(t) * self.frame_bytes + 4
+            raw[k] = self._mm[o:o + 48].view(self._e + "f8")
+        L = raw[:, [0, 2, 5]]
+        ang = raw[:, [4, 3, 1]]
+        if np.all(np.abs(ang) <= 1.0):
+            ang = np.degrees(np.arccos(ang))
+        return L, ang
+
+    def close(self):
+        self._mm = None
+
+
+def write_dcd(path: str, xyz: np.ndarray, cell_lengths=None, cell_angles=None, big_endian: bool = False,
+              cosines: bool = False) -> None:
+    """Minimal CHARMM-style DCD writer (tests and fixtures): optional unit cell, either byte order."""
+    xyz = np.asarray(xyz, dtype=np.float32)
+    T, N, _ = xyz.shape
+    e = ">" if big_endian else "<"
+    i4 = lambda *v: np.array(v, dtype=e + "i4").tobytes()
+    icntrl = np.zeros(20, dtype=e + "i4")
+    icntrl[0], icntrl[1], icntrl[2], icntrl[19] = T, 1, 1, 24
+    icntrl[10] = 1 if cell_lengths is not None else 0
+    title = b"CAVIAR_B200 TEST FIXTURE".ljust(80)
+    with open(path, "wb") as fh:
+        fh.write(i4(84) + b"CORD" + icntrl.tobytes() + i4(84))
+        fh.write(i4(84) + i4(1) + title + i4(84))
+        fh.write(i4(4) + i4(N) + i4(4))
+        if cell_lengths is not None:
+            L = np.broadcast_to(np.asarray(cell_lengths, dtype=np.float64), (T, 3))
+            A = np.broadcast_to(np.asarray(cell_angles if cell_angles is not None else [90.0] * 3, dtype=np.float64), (T, 3))
+            if cosines:
+                A = np.cos(np.radians(A))
+        for t in range(T):
+            if cell_lengths is not None:
+                rec = np.array([L[t, 0], A[t, 2], L[t, 1], A[t, 1], A[t, 0], L[t, 2]], dtype=e + "f8")
+                fh.write(i4(48) + rec.tobytes() + i4(48))
+            for c in range(3):
+                fh.write(i4(4 * N) + xyz[t, :, c].astype(e + "f4").tobytes() + i4(4 * N))
 
 
 def write_netcdf(path: str, xyz: np.ndarray, cell_lengths=None, cell_angles=None) -> None:

@@ -219,6 +219,13 @@ void caviar_release_cache(void);
 int caviar_compact_frames_host(const void* src, int64_t n_frames, int64_t frame_stride_bytes, int32_t n_atoms,
                                const int32_t* atoms, int64_t n_sel, int32_t big_endian, float* out);
 
+/* The same for formats that keep a frame as three separate coordinate arrays (DCD: X[N], Y[N], Z[N], each inside a
+ * Fortran record): x_off / y_off / z_off = byte offsets of those arrays inside a frame; byte_swap != 0 when the file's
+ * byte order is not the host's. */
+int caviar_compact_frames_soa_host(const void* src, int64_t n_frames, int64_t frame_stride_bytes, int32_t n_atoms,
+                                   int64_t x_off, int64_t y_off, int64_t z_off, const int32_t* atoms,
+                                   int64_t n_sel, int32_t byte_swap, float* out);
+
 /* Host-side CSV row formatter for the Extractor output (CAVIAR_Distances-Extractor.py:147-151,196-198: one frame
  * column, then one distance column per pair).  Formats rows x cols float32 values as
  *     "<first_index + r*index_step>,<v>,<v>,...\n"      with `decimals` fixed decimals (printf "%.Nf" rounding)

@@ -202,3 +202,35 @@ def test_native_frame_compaction_equals_numpy(tmp_path, fmt):
     with pytest.raises(Exception):
         tr.coords_of(np.array([N]), 0, T)
     tr.close()
+
+
+@pytest.mark.parametrize("big,cell,cosines", [(False, None, False), (True, "ortho", False), (False, "tric", True), (True, "tric", False)])
+def test_dcd_trajectories(tmp_path, big, cell, cosines):
+    """CHARMM / NAMD DCD: header, either byte order, optional unit cell (degrees or cosines), native gather of the
+    selected atoms out of the X / Y / Z records."""
+    from caviar_b200 import trajio
+    rng = np.random.default_rng(7)
+    T, N = 19, 83
+    xyz = rng.normal(0, 25, size=(T, N, 3)).astype(np.float32)
+    L = rng.uniform(40, 60, size=(T, 3))
+    ang = {"ortho": [90.0, 90.0, 90.0], "tric": [80.0, 95.0, 109.4712206]}.get(cell)
+    path = str(tmp_path / "t.dcd")
+    trajio.write_dcd(path, xyz, L if cell else None, ang, big_endian=big, cosines=cosines)
+    tr = trajio.Trajectory(path)
+    assert (tr.n_frames, tr.n_atoms) == (T, N)
+    assert tr.box_kind() == {None: None, "ortho": "ortho", "tric": "triclinic"}[cell]
+    atoms = np.array([82, 0, 5, 5, 41])
+    for lo, hi, stride in ((0, T, 1), (3, 18, 4), (7, 8, 1)):
+        got = tr.coords_of(atoms, lo, hi, stride)
+        assert got.tobytes() == np.ascontiguousarray(xyz[lo:hi:stride][:, atoms, :]).tobytes()
+    assert tr.coords(2, 5).tobytes() == xyz[2:5].tobytes()
+    if cell == "ortho":
+        np.testing.assert_allclose(tr.cell(0, T, 2), L[::2].astype(np.float32))
+    elif cell == "tric":
+        want = trajio.cell_to_matrix(L[1:9:3], np.broadcast_to(ang, (3, 3)))
+        np.testing.assert_allclose(tr.cell(1, 9, 3), want.astype(np.float32), rtol=1e-6, atol=1e-5)
+    tr.close()
+    bad = tmp_path / "bad.dcd"
+    bad.write_bytes(b"\\x00" * 200)
+    with pytest.raises(ValueError):
+        trajio.Trajectory(str(bad))

@@ -10,7 +10,7 @@ from oracle import caviar_oracle as orc
 pytestmark = pytest.mark.gpu
 
 
-def _system(tmp_path, box):
+def _system(tmp_path, box, fmt="nc"):
     from caviar_b200 import trajio
     rng = np.random.default_rng(9)
     n_res, T = 60, 53
@@ -26,21 +26,23 @@ def _system(tmp_path, box):
     xyz = ((base[None] + rng.normal(0, 0.4, size=(T, n_atoms, 3))) % L).astype(np.float32)
     top = str(tmp_path / "sys.prmtop")
     trajio.write_prmtop(top, names, labels, first)
-    nc = str(tmp_path / "traj.nc")
+    nc = str(tmp_path / f"traj.{fmt}")
+    write = trajio.write_netcdf if fmt == "nc" else trajio.write_dcd
     if box == "ortho":
-        trajio.write_netcdf(nc, xyz, L)
+        write(nc, xyz, L)
     elif box == "triclinic":
-        trajio.write_netcdf(nc, xyz, L, [109.4712206] * 3)
+        write(nc, xyz, L, [109.4712206] * 3)
     else:
-        trajio.write_netcdf(nc, xyz)
+        write(nc, xyz)
     ca = np.array([f + 2 for f in first])
     return top, nc, xyz, L, ca, labels
 
 
-@pytest.mark.parametrize("box,stride", [("ortho", 1), ("triclinic", 2), (None, 3)])
-def test_extractor_cli_against_oracle(tmp_path, capsys, box, stride):
+@pytest.mark.parametrize("box,stride,fmt", [("ortho", 1, "nc"), ("triclinic", 2, "nc"), (None, 3, "nc"),
+                                            ("triclinic", 1, "dcd"), (None, 2, "dcd")])
+def test_extractor_cli_against_oracle(tmp_path, capsys, box, stride, fmt):
     from caviar_b200 import extractor, trajio
-    top, nc, xyz, L, ca, labels = _system(tmp_path, box)
+    top, nc, xyz, L, ca, labels = _system(tmp_path, box, fmt)
     offset = 21
     # the ranked-loading CSV CAVIAR-1.0.py writes (save_tic_csv, :141-147) is a valid --pairs-file
     sel = [(0, 9), (3, 40), (59, 12), (7, 8), (3, 40)]
