@@ -6,8 +6,8 @@ Here the two formats that workflow uses are read directly:
 * Amber NetCDF trajectories (``.nc``; NetCDF-3, 64-bit offset): ``coordinates (frame, atom, 3)`` float32 Angstrom,
   ``cell_lengths`` / ``cell_angles (frame, 3)`` float64 -- through ``scipy.io.netcdf_file(mmap=True)``, so frame
   blocks are paged in on demand and never copied as a whole;
-* Amber prmtop topologies (``%FLAG ATOM_NAME / RESIDUE_LABEL / RESIDUE_POINTER``) and PDB files, only as far as
-  the ``:{idx}@CA`` / ``resid {n}@CA`` selections of the reference need (Extractor:127-138).
+* Amber prmtop topologies (``%FLAG ATOM_NAME / RESIDUE_LABEL / RESIDUE_POINTER``), PDB files and CHARMM / NAMD PSF
+  files, only as far as the ``:{idx}@CA`` / ``resid {n}@CA`` selections of the reference need (Extractor:127-138).
 
 * CHARMM / NAMD DCD trajectories (``.dcd``): Fortran-record file, per frame an optional unit-cell record (6 doubles)
   and three float32 arrays X[N], Y[N], Z[N]; either byte order; memory-mapped, the selected atoms are gathered
@@ -125,10 +125,41 @@ def read_pdb(path: str) -> Topology:
     return Topology(names, labels, first, seqs)
 
 
+def read_psf(path: str) -> Topology:
+    """CHARMM / NAMD / X-PLOR PSF (what usually accompanies a DCD): the ``!NATOM`` section, whitespace separated
+    ``atomid segid resid resname atomname ...``; a residue changes when (segid, resid) does."""
+    names, labels, first, seqs = [], [], [], []
+    with open(path, "r", errors="ignore") as fh:
+        lines = iter(fh)
+        n_atom = None
+        for line in lines:
+            if "!NATOM" in line:
+                n_atom = int(line.split()[0])
+                break
+        if n_atom is None:
+            raise ValueError(f"{path}: no !NATOM section (not a PSF file)")
+        last = None
+        for _ in range(n_atom):
+            f = next(lines).split()
+            if len(f) < 5:
+                raise ValueError(f"{path}: short atom record")
+            key = (f[1], f[2])
+            if key != last:
+                last = key
+                first.append(len(names))
+                labels.append(f[3][:3] if len(f[3]) > 3 else f[3])
+                digits = "".join(ch for ch in f[2] if ch.isdigit() or ch == "-")     # resid may carry an insertion code
+                seqs.append(int(digits) if digits not in ("", "-") else len(first))
+            names.append(f[4])
+    return Topology(names, labels, first, seqs)
+
+
 def read_topology(path: str) -> Topology:
     ext = os.path.splitext(path)[1].lower()
     if ext in (".pdb", ".ent"):
         return read_pdb(path)
+    if ext == ".psf":
+        return read_psf(path)
     return read_prmtop(path)
 
 

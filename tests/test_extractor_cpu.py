@@ -234,3 +234,24 @@ def test_dcd_trajectories(tmp_path, big, cell, cosines):
     bad.write_bytes(b"\\x00" * 200)
     with pytest.raises(ValueError):
         trajio.Trajectory(str(bad))
+
+
+def test_psf_topology(ext, tmp_path):
+    """CHARMM / NAMD PSF next to a DCD: residues from (segid, resid), CA selection as with prmtop / PDB."""
+    from caviar_b200 import trajio
+    rows, k = [], 0
+    for seg, resids in (("PROA", [5, 6, 7]), ("PROB", [5, 9])):
+        for r in resids:
+            for name in ("N", "HN", "CA", "C", "O"):
+                k += 1
+                rows.append(f"{k:10d} {seg:8s} {r:<8d} {'ASP' if r % 2 else 'GLUP':8s} {name:8s} {'NH1':6s} {-0.47:10.6f} {14.007:13.4f} {0:11d}")
+    psf = tmp_path / "sys.psf"
+    psf.write_text("PSF EXT CMAP\n\n         1 !NTITLE\n* test\n\n" + f"{k:10d} !NATOM\n" + "\n".join(rows) + "\n\n         0 !NBOND: bonds\n")
+    top = trajio.read_topology(str(psf))
+    assert top.n_atoms == 25 and top.n_res == 5
+    assert top.res_labels == ["ASP", "GLU", "ASP", "ASP", "ASP"] and top.res_seq == [5, 6, 7, 5, 9]
+    assert [top.atom_of(r) for r in range(5)] == [2, 7, 12, 17, 22]
+    atoms = ext.select_atoms(top, [("ASP", 1, "GLU", 2), ("ASP", 4, "ASP", 5)], "sequential", 0)
+    assert atoms.tolist() == [[2, 7], [17, 22]]
+    with pytest.raises(ValueError):
+        trajio.read_psf(str(tmp_path / "sys.psf").replace("sys", "nope")) if False else trajio.read_psf(__file__)
