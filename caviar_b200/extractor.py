@@ -135,8 +135,8 @@ def format_rows(values: np.ndarray, first_index: int, step: int, decimals: int) 
 
 def build_parser() -> argparse.ArgumentParser:
     ap = argparse.ArgumentParser(description="Distanze CA-CA per frame su GPU B200 (drop-in di CAVIAR_Distances-Extractor.py).")
-    ap.add_argument("--top", required=True, help="Topologia (parm7/prmtop/pdb/psf)")
-    ap.add_argument("--traj", required=True, help="Traiettoria MD (Amber NetCDF .nc, CHARMM/NAMD .dcd, oppure .npy (T,N,3))")
+    ap.add_argument("--top", required=True, help="Topologia (parm7/prmtop/pdb/psf/gro)")
+    ap.add_argument("--traj", required=True, help="Traiettoria MD (Amber NetCDF .nc, CHARMM/NAMD .dcd, GROMACS .trr, oppure .npy (T,N,3))")
     ap.add_argument("--pairs-file", help="File testo con coppie tipo ASP25-GLU216")
     ap.add_argument("--pairs", help='Coppie comma-separated, es: "ASP25-GLU216,ALA15-GLY26"')
     ap.add_argument("--numbering", default="sequential", choices=["sequential", "resSeq"],

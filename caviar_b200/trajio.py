@@ -13,6 +13,9 @@ Here the two formats that workflow uses are read directly:
   and three float32 arrays X[N], Y[N], Z[N]; either byte order; memory-mapped, the selected atoms are gathered
   natively.  Files with fixed atoms (NAMNF > 0) or 4-D coordinates are refused.
 
+* GROMACS TRR trajectories (``.trr``; XDR, big-endian, single precision, constant frame size): coordinates and box
+  in nm are converted to Angstrom (x10) after the gather.  ``.gro`` files serve as topologies.
+
 A ``.npy`` array ``(T, N, 3)`` is accepted as a trajectory too (no box), which is what the tests and benchmarks use
 when no NetCDF file is at hand.
 """
@@ -154,12 +157,35 @@ def read_psf(path: str) -> Topology:
     return Topology(names, labels, first, seqs)
 
 
+def read_gro(path: str) -> Topology:
+    """GROMACS .gro (fixed columns: resid[0:5] resname[5:10] atomname[10:15] atomnr[15:20] ...): first frame only."""
+    names, labels, first, seqs = [], [], [], []
+    with open(path, "r", errors="ignore") as fh:
+        fh.readline()
+        n_atom = int(fh.readline().split()[0])
+        last = None
+        for _ in range(n_atom):
+            line = fh.readline()
+            if len(line) < 20:
+                raise ValueError(f"{path}: short atom line")
+            key = (line[0:5], line[5:10])
+            if key != last:
+                last = key
+                first.append(len(names))
+                labels.append(line[5:10].strip()[:3])
+                seqs.append(int(line[0:5]))
+            names.append(line[10:15].strip())
+    return Topology(names, labels, first, seqs)
+
+
 def read_topology(path: str) -> Topology:
     ext = os.path.splitext(path)[1].lower()
     if ext in (".pdb", ".ent"):
         return read_pdb(path)
     if ext == ".psf":
         return read_psf(path)
+    if ext == ".gro":
+        return read_gro(path)
     return read_prmtop(path)
 
 
@@ -213,6 +239,13 @@ class Trajectory:
         ext = os.path.splitext(path)[1].lower()
         self._nc = None
         self._dcd = None
+        self._trr = None
+        if ext == ".trr":
+            self._trr = _TrrFile(path)
+            self._xyz = None
+            self._len = self._ang = None
+            self.n_frames, self.n_atoms = self._trr.n_frames, self._trr.n_atoms
+            return
         if ext == ".dcd":
             self._dcd = _DcdFile(path)
             self._xyz = None
@@ -236,6 +269,8 @@ class Trajectory:
 
     @property
     def has_box(self) -> bool:
+        if self._trr is not None:
+            return self._trr.has_box and self.n_frames > 0 and bool(np.all(np.diag(self._trr.box(0, 1)[0]) > 0))
         if self._dcd is not None:
             return self._dcd.has_cell and self.n_frames > 0 and bool(np.all(self._dcd.cell(0, 1)[0][0] > 0))
         if self._len is None or self._ang is None or self.n_frames == 0:
@@ -245,11 +280,15 @@ class Trajectory:
     def box_kind(self) -> Optional[str]:
         if not self.has_box:
             return None
+        if self._trr is not None:
+            h = self._trr.box(0, 1)[0]
+            off = np.abs(h - np.diag(np.diag(h))).max()
+            return "ortho" if off <= 1e-6 * np.abs(np.diag(h)).max() else "triclinic"
         ang = self._dcd.cell(0, 1)[1][0] if self._dcd is not None else np.asarray(self._ang[0], dtype=np.float64)
         return "ortho" if np.allclose(ang, 90.0, atol=1e-6) else "triclinic"
 
     def coords(self, lo: int, hi: int, stride: int = 1) -> np.ndarray:
-        if self._dcd is not None:
+        if self._dcd is not None or self._trr is not None:
             return self.coords_of(np.arange(self.n_atoms), lo, hi, stride)
         return np.ascontiguousarray(self._xyz[lo:hi:stride], dtype=np.float32)
 
@@ -263,6 +302,13 @@ class Trajectory:
         n = len(range(lo, hi, stride))
         if out is None:
             out = np.empty((n, len(atoms), 3), dtype=np.float32)
+        if self._trr is not None:
+            if n and len(atoms):
+                r = self._trr
+                _lib.check(_lib.lib.caviar_compact_frames_host(r.x_ptr(lo), n, r.frame_bytes * stride, r.n_atoms,
+                                                               atoms.ctypes.data, len(atoms), 1 if r.big else 0, out.ctypes.data))
+                out *= np.float32(10.0)                              # nm -> Angstrom
+            return out
         if self._dcd is not None:
             if n and len(atoms):
                 d = self._dcd
@@ -286,6 +332,10 @@ class Trajectory:
         kind = self.box_kind()
         if kind is None:
             return None
+        if self._trr is not None:
+            h = self._trr.box(lo, hi, stride) * 10.0                 # nm -> Angstrom; rows = box vectors (a along x)
+            return np.stack([h[:, 0, 0], h[:, 1, 1], h[:, 2, 2]], axis=1).astype(np.float32) if kind == "ortho" \
+                else h.astype(np.float32)
         if self._dcd is not None:
             L, A = self._dcd.cell(lo, hi, stride)
         else:
@@ -296,6 +346,9 @@ class Trajectory:
         return cell_to_matrix(L, A).astype(np.float32)
 
     def close(self):
+        if self._trr is not None:
+            self._trr.close()
+            self._trr = None
         if self._dcd is not None:
             self._dcd.close()
             self._dcd = None
@@ -306,6 +359,82 @@ class Trajectory:
             except Exception:
                 pass
             self._nc = None
+
+
+class _TrrFile:
+    """Layout of a GROMACS TRR file (XDR: big-endian) over a read-only memory map; single precision, every frame of
+    the same size (the common case: positions, optionally velocities / forces, written at one interval)."""
+
+    _INTS = ("ir", "e", "box", "vir", "pres", "top", "sym", "x", "v", "f", "natoms", "step", "nre")
+
+    def __init__(self, path: str):
+        self._mm = np.memmap(path, dtype=np.uint8, mode="r")
+        self.big = sys.byteorder != "big"                        # file is big-endian: swap on little-endian hosts
+        h = self._header(0)
+        if h["x"] == 0:
+            raise ValueError(f"{path}: the first TRR frame carries no coordinates")
+        real = h["x"] // (3 * h["natoms"])
+        if real != 4:
+            raise ValueError(f"{path}: double-precision TRR files are not supported")
+        self.n_atoms = h["natoms"]
+        self.has_box = h["box"] == 36
+        self.header_bytes = h["_header"]
+        self.box_off = self.header_bytes
+        self.x_off = self.header_bytes + h["box"] + h["vir"] + h["pres"]
+        self.frame_bytes = self.x_off + h["x"] + h["v"] + h["f"]
+        self.n_frames = self._mm.size // self.frame_bytes
+        for t in (1, self.n_frames - 1):
+            if 0 < t < self.n_frames:
+                g = self._header(t * self.frame_bytes)
+                if any(g[k] != h[k] for k in ("box", "vir", "pres", "x", "v", "f", "natoms")):
+                    raise ValueError(f"{path}: TRR frames of different sizes are not supported")
+
+    def _header(self, pos: int) -> dict:
+        mm = self._mm
+        if int(mm[pos:pos + 4].view(">i4")[0]) != 1993:
+            raise ValueError("not a TRR file (magic number 1993 missing)")
+        slen = int(mm[pos + 8:pos + 12].view(">i4")[0])
+        p = pos + 12 + (slen + 3) // 4 * 4
+        vals = mm[p:p + 52].view(">i4")
+        h = {k: int(v) for k, v in zip(self._INTS, vals)}
+        real = 8 if (h["box"] == 72 or (h["box"] == 0 and h["natoms"] and h["x"] // (3 * h["natoms"]) == 8)) else 4
+        h["_header"] = (p + 52 + 2 * real) - pos
+        return h
+
+    def x_ptr(self, t: int) -> int:
+        return self._mm.ctypes.data + t * self.frame_bytes + self.x_off
+
+    def box(self, lo: int, hi: int, stride: int = 1) -> np.ndarray:
+        idx = np.arange(lo, hi, max(1, stride))
+        out = np.empty((len(idx), 3, 3), dtype=np.float64)
+        for k, t in enumerate(idx):
+            o = int(t) * self.frame_bytes + self.box_off
+            out[k] = self._mm[o:o + 36].view(">f4").reshape(3, 3)
+        return out
+
+    def close(self):
+        self._mm = None
+
+
+def write_trr(path: str, xyz_nm: np.ndarray, box_nm=None, with_velocities: bool = False) -> None:
+    """Minimal single-precision TRR writer (tests and fixtures): coordinates / box in nm."""
+    xyz_nm = np.asarray(xyz_nm, dtype=np.float32)
+    T, N, _ = xyz_nm.shape
+    i4 = lambda *v: np.array(v, dtype=">i4").tobytes()
+    with open(path, "wb") as fh:
+        for t in range(T):
+            box_b = 36 if box_nm is not None else 0
+            v_b = 12 * N if with_velocities else 0
+            fh.write(i4(1993, 13, 12) + b"GMX_trn_file")
+            fh.write(i4(0, 0, box_b, 0, 0, 0, 0, 12 * N, v_b, 0, N, t, 0))
+            fh.write(np.array([float(t), 0.0], dtype=">f4").tobytes())
+            if box_nm is not None:
+                b = np.asarray(box_nm, dtype=np.float64)
+                b = b[t] if b.ndim == 3 else b
+                fh.write(np.asarray(b, dtype=">f4").tobytes())
+            fh.write(xyz_nm[t].astype(">f4").tobytes())
+            if with_velocities:
+                fh.write(np.zeros((N, 3), dtype=">f4").tobytes())
 
 
 class _DcdFile:

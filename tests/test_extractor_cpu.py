@@ -255,3 +255,39 @@ def test_psf_topology(ext, tmp_path):
     assert atoms.tolist() == [[2, 7], [17, 22]]
     with pytest.raises(ValueError):
         trajio.read_psf(str(tmp_path / "sys.psf").replace("sys", "nope")) if False else trajio.read_psf(__file__)
+
+
+@pytest.mark.parametrize("box,vel", [(None, False), ("ortho", True), ("tric", False)])
+def test_trr_trajectories_and_gro_topology(ext, tmp_path, box, vel):
+    """GROMACS TRR (XDR, nm) -> Angstrom, box rows = lattice vectors; .gro as topology."""
+    from caviar_b200 import trajio
+    rng = np.random.default_rng(3)
+    T, N = 11, 37
+    x_nm = rng.normal(0, 2.5, size=(T, N, 3)).astype(np.float32)
+    h = None
+    if box == "ortho":
+        h = np.diag([4.0, 5.0, 6.0])
+    elif box == "tric":
+        h = np.array([[5.0, 0, 0], [1.0, 4.5, 0], [-0.5, 1.5, 4.0]])
+    path = str(tmp_path / "t.trr")
+    trajio.write_trr(path, x_nm, h, with_velocities=vel)
+    tr = trajio.Trajectory(path)
+    assert (tr.n_frames, tr.n_atoms) == (T, N)
+    assert tr.box_kind() == {None: None, "ortho": "ortho", "tric": "triclinic"}[box]
+    atoms = np.array([36, 0, 7, 7])
+    got = tr.coords_of(atoms, 1, 10, 3)
+    assert got.tobytes() == (x_nm[1:10:3][:, atoms, :] * np.float32(10.0)).tobytes()
+    assert tr.coords(0, 2).shape == (2, N, 3)
+    if box == "ortho":
+        np.testing.assert_allclose(tr.cell(0, T), np.broadcast_to([40.0, 50.0, 60.0], (T, 3)))
+    elif box == "tric":
+        np.testing.assert_allclose(tr.cell(2, 4), np.broadcast_to(h * 10.0, (2, 3, 3)), rtol=1e-6)
+    tr.close()
+    gro = tmp_path / "s.gro"
+    lines = ["test", f"{6:5d}"]
+    for k, (rid, rn, an) in enumerate([(1, "ASP", "N"), (1, "ASP", "CA"), (1, "ASP", "C"), (2, "GLU", "N"), (2, "GLU", "CA"), (2, "GLU", "C")], 1):
+        lines.append(f"{rid:5d}{rn:<5s}{an:>5s}{k:5d}{0.1 * k:8.3f}{0.0:8.3f}{0.0:8.3f}")
+    gro.write_text("\n".join(lines) + "\n   4.00000   5.00000   6.00000\n")
+    top = trajio.read_topology(str(gro))
+    assert top.n_atoms == 6 and top.res_labels == ["ASP", "GLU"] and [top.atom_of(0), top.atom_of(1)] == [1, 4]
+    assert ext.select_atoms(top, [("ASP", 1, "GLU", 2)], "resSeq", 0).tolist() == [[1, 4]]
