@@ -20,6 +20,7 @@ CV_OK, CV_E_INVALID, CV_E_CUDA, CV_E_NO_DEVICE, CV_E_UNSUPPORTED, CV_E_NOMEM = 0
 BOX_NONE, BOX_ORTHO, BOX_TRICLINIC = 0, 1, 2
 PLAN_FORCE_DIRECT, PLAN_FORCE_STAGED = 1, 2
 MODE_DIRECT, MODE_ZEROCOPY, MODE_STAGED = 0, 1, 2
+ORDER_CALLER, ORDER_PLAN = 0, 1
 MODE_NAMES = {MODE_DIRECT: "direct", MODE_ZEROCOPY: "zerocopy", MODE_STAGED: "staged"}
 
 
@@ -73,14 +74,14 @@ SYMBOLS = {
     "caviar_plan_destroy": (None, [C.c_void_p]),
     "caviar_plan_info": (C.c_int, [C.c_void_p, C.POINTER(CvPlanInfo)]),
     "caviar_prepare_box": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
-    "caviar_stage_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "caviar_plan_status": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "caviar_plan_atom_order": (C.c_int64, [C.POINTER(CvPlanDesc), C.c_int32, C.c_void_p, C.c_int64]),
+    "caviar_stage_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "caviar_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                              C.POINTER(CvFrameOutputs), C.POINTER(CvAggregates), C.c_void_p, C.c_void_p]),
     "caviar_last_launch_count": (C.c_int64, []),
     "caviar_weighted_scores": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "caviar_features_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
-                                       C.POINTER(CvHostOutputs), C.c_int64]),
+                                       C.POINTER(CvHostOutputs), C.c_int64, C.c_int32]),
     "caviar_pair_distances_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "caviar_release_cache": (None, []),
     "caviar_pair_distances_host_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
@@ -89,7 +90,7 @@ SYMBOLS = {
     "caviar_compact_frames_soa_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64,
                                                C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "caviar_format_csv": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
-                                      C.c_void_p, C.c_int64]),
+                                      C.c_int32, C.c_void_p, C.c_int64]),
     "caviar_last_error": (C.c_char_p, []),
     "caviar_abi_version": (C.c_int, []),
 }

@@ -152,7 +152,7 @@ extern "C" int caviar_plan_describe(const CvPlanDesc* desc, int32_t n_sms, CvPla
 }
 
 // Host-side planning only: the layout tables themselves, for tests that check the planner without a GPU.
-//   tile_desc : [n_tiles][8] int32 = {kind, f_begin, n_feat, idx_off, grp_off, grp_floats, fixed_point, 0}
+//   tile_desc : [n_tiles][8] int32 = {kind, f_begin, n_feat, idx_off, grp_off, grp_floats, 0, 0}
 //   idx       : [3][n_tiles * 896] int32, float offset (3 * slot) of atom role 0 / 1 / 2 inside the tile's block
 //   src_off   : [staged_floats_per_frame] int32, staged float j <- float src_off[j] of the input frame
 // Pass NULL buffers to query the sizes (n_tiles via CvPlanInfo, src_off length = staged_floats_per_frame).
@@ -218,8 +218,8 @@ extern "C" int caviar_plan_create(const CvPlanDesc* desc, CvPlan** out) {
     if (e == cudaSuccess) e = upload(&p->d_idx1, p->hp.idx1);
     if (e == cudaSuccess) e = upload(&p->d_idx2, p->hp.idx2);
     if (e == cudaSuccess) e = upload(&p->d_src_off, p->hp.src_off);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_err, 2 * sizeof(int));      // [0] box set-up, [1] staging (sticky)
-    if (e == cudaSuccess) e = cudaMemset(p->d_err, 0, 2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_err, sizeof(int));          // box set-up errors
+    if (e == cudaSuccess) e = cudaMemset(p->d_err, 0, sizeof(int));
     if (e != cudaSuccess) {
         std::string msg = std::string("plan upload: ") + cudaGetErrorString(e);
         caviar_plan_destroy(p);
@@ -233,6 +233,20 @@ extern "C" int caviar_plan_info(const CvPlan* plan, CvPlanInfo* info) {
     if (!plan || !info) return fail(CV_E_INVALID, "null argument");
     fill_info(plan->hp, *info);
     return CV_OK;
+}
+
+// The plan order: slot k of a plan-order (staged) frame holds atom order[k] of the caller's frame.  Host-side only.
+extern "C" int64_t caviar_plan_atom_order(const CvPlanDesc* desc, int32_t n_sms, int32_t* order, int64_t cap) {
+    if (!desc) return fail(CV_E_INVALID, "null argument");
+    HostPlan hp;
+    std::string why = build_plan(*desc, n_sms, hp);
+    if (!why.empty()) return fail(CV_E_INVALID, why);
+    const int64_t n = hp.staged_floats / 3;
+    if (order) {
+        if (cap < n) return fail(CV_E_INVALID, "atom order buffer too small");
+        for (int64_t k = 0; k < n; ++k) order[k] = hp.src_off[3 * k] / 3;
+    }
+    return n;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -262,7 +276,7 @@ extern "C" int caviar_prepare_box(const CvPlan* plan, const float* box_dev, int6
 }
 
 extern "C" int caviar_stage_frames(const CvPlan* plan, const float* xyz_dev, int64_t frame_stride_floats,
-                                   int64_t n_frames, float* staged_dev, const float* boxrec_dev, void* stream) {
+                                   int64_t n_frames, float* staged_dev, void* stream) {
     if (!plan) return fail(CV_E_INVALID, "null plan");
     g_launches = 0;
     const HostPlan& hp = plan->hp;
@@ -271,23 +285,6 @@ extern "C" int caviar_stage_frames(const CvPlan* plan, const float* xyz_dev, int
     if (!xyz_dev || !staged_dev) return fail(CV_E_INVALID, "null coordinate pointer");
     if (frame_stride_floats < 3ll * hp.desc.n_atoms) return fail(CV_E_INVALID, "frame stride smaller than 3*n_atoms");
     if ((reinterpret_cast<uintptr_t>(staged_dev) & 15) != 0) return fail(CV_E_INVALID, "staged buffer must be 16-byte aligned");
-    const bool periodic = hp.desc.box_kind != CV_BOX_NONE;
-    if (periodic && !boxrec_dev)
-        return fail(CV_E_INVALID, "periodic plan: caviar_stage_frames needs the frames' box records (caviar_prepare_box) -- "
-                                  "atoms are wrapped into the cell and triplet blocks become fractional coordinates");
-    if (periodic) {
-        const int n_slots = (int)(hp.staged_floats / 3), first_frac = (int)(hp.frac_begin / 3);
-        const int per_block = 256 * kPeriodicAtomsPerThread;
-        for (int64_t t0 = 0; t0 < n_frames; t0 += 65535) {               // one block row per frame (grid.y <= 65535)
-            const int64_t n = std::min<int64_t>(65535, n_frames - t0);
-            stage_periodic_kernel<<<dim3((n_slots + per_block - 1) / per_block, (unsigned)n), 256, 0, (cudaStream_t)stream>>>(
-                xyz_dev + t0 * frame_stride_floats, frame_stride_floats, n, plan->d_src_off, n_slots, first_frac,
-                hp.staged_floats, boxrec_dev + t0 * kRecFloats, staged_dev + t0 * hp.staged_floats, plan->d_err + 1);
-            CV_CUDA(cudaGetLastError());
-            g_launches += 1;
-        }
-        return CV_OK;
-    }
     const int S4 = (int)(hp.staged_floats / 4);
     const int64_t chunk = 65535ll * kStageFramesPerThread;     // grid.y is limited to 65535 blocks
     for (int64_t t0 = 0; t0 < n_frames; t0 += chunk) {
@@ -303,26 +300,12 @@ extern "C" int caviar_stage_frames(const CvPlan* plan, const float* xyz_dev, int
     return CV_OK;
 }
 
-// Sticky staging errors (set asynchronously by K0): synchronises `stream`, reports and clears them.
-extern "C" int caviar_plan_status(const CvPlan* plan, void* stream) {
-    if (!plan) return fail(CV_E_INVALID, "null plan");
-    int err = 0;
-    CV_CUDA(cudaMemcpyAsync(&err, plan->d_err + 1, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-    CV_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-    if (err) {
-        CV_CUDA(cudaMemsetAsync(plan->d_err + 1, 0, sizeof(int), (cudaStream_t)stream));
-        return fail(CV_E_INVALID, "non-finite coordinate in an atom of a triplet (periodic plans stage those as fixed-point "
-                                  "fractional coordinates, which cannot carry NaN / Inf): the angles of the affected frames are meaningless");
-    }
-    return CV_OK;
-}
-
 // ------------------------------------------------------------------------------------------------
 // the fused run
 // ------------------------------------------------------------------------------------------------
-template <int BOX, bool PIPE, bool FRAC, bool LEAN>
+template <int BOX, bool PIPE, bool LEAN>
 static cudaError_t launch_features(const CvPlan* plan, const RunParams& rp, cudaStream_t st) {
-    auto kern = features_kernel<BOX, PIPE, FRAC, LEAN>;
+    auto kern = features_kernel<BOX, PIPE, LEAN>;
     const int threads = PIPE ? kConsumerThreads + kProducerThreads : kConsumerThreads;
     const int smem = PIPE ? plan->hp.smem_bytes : 0;
     if (PIPE) {
@@ -368,17 +351,20 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
     rp.boxrec = boxrec_dev;
     rp.n_frames = n_frames;
     if (hp.mode == CV_MODE_STAGED) {
-        rp.frame_stride = hp.staged_floats;
+        // plan-order frames: densely packed unless the caller says otherwise (0 = dense)
+        rp.frame_stride = frame_stride_floats > 0 ? frame_stride_floats : hp.staged_floats;
+        if (rp.frame_stride < hp.staged_floats || rp.frame_stride % 4 != 0)
+            return fail(CV_E_INVALID, "plan-order frames: stride must be >= staged_floats_per_frame and a multiple of 4 floats");
     } else {
         if (frame_stride_floats < 3ll * hp.desc.n_atoms) return fail(CV_E_INVALID, "frame stride smaller than 3*n_atoms");
         if (hp.mode == CV_MODE_ZEROCOPY && frame_stride_floats != 3ll * hp.desc.n_atoms)
             return fail(CV_E_INVALID, "zero-copy mode needs densely packed frames (stride == 3*n_atoms)");
         rp.frame_stride = frame_stride_floats;
     }
-    if (hp.mode != CV_MODE_DIRECT) {
-        if ((reinterpret_cast<uintptr_t>(coords_dev) & 15) != 0) return fail(CV_E_INVALID, "coordinates must be 16-byte aligned for TMA");
-        if (boxrec_dev && (reinterpret_cast<uintptr_t>(boxrec_dev) & 15) != 0) return fail(CV_E_INVALID, "box records must be 16-byte aligned");
-    }
+    if (hp.mode != CV_MODE_DIRECT && (reinterpret_cast<uintptr_t>(coords_dev) & 15) != 0)
+        return fail(CV_E_INVALID, "coordinates must be 16-byte aligned for TMA");
+    // every flavour reads the record's head with 128-bit loads (and TMA copies it whole in the ring flavours)
+    if (boxrec_dev && (reinterpret_cast<uintptr_t>(boxrec_dev) & 15) != 0) return fail(CV_E_INVALID, "box records must be 16-byte aligned");
     rp.tiles = plan->d_tiles;
     rp.idx0 = plan->d_idx0; rp.idx1 = plan->d_idx1; rp.idx2 = plan->d_idx2;
     rp.n_tiles = (int)hp.tiles.size();
@@ -429,20 +415,16 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
     if (rp.score) CV_CUDA(cudaMemsetAsync(rp.score, 0, sizeof(int32_t) * n_frames, st));
 
     cudaError_t e;
-    // TMA ring unless the plan gathers from global memory (raw frames, or K0's compact frame of a large overlapping
-    // selection); staged periodic plans carry fixed-point triplet blocks
-    const bool pipe = hp.mode != CV_MODE_DIRECT && !hp.gather_global;
-    const bool frac = hp.mode == CV_MODE_STAGED && hp.desc.box_kind != CV_BOX_NONE;
-#define CV_LAUNCH(B, P_, F_) (lean ? launch_features<B, P_, F_, true>(plan, rp, st) : launch_features<B, P_, F_, false>(plan, rp, st))
-    switch (hp.desc.box_kind * 4 + (pipe ? 2 : 0) + (frac ? 1 : 0)) {
-        case 0: e = CV_LAUNCH(0, false, false); break;
-        case 2: e = CV_LAUNCH(0, true, false); break;
-        case 4: e = CV_LAUNCH(1, false, false); break;
-        case 5: e = CV_LAUNCH(1, false, true); break;
-        case 7: e = CV_LAUNCH(1, true, true); break;
-        case 8: e = CV_LAUNCH(2, false, false); break;
-        case 9: e = CV_LAUNCH(2, false, true); break;
-        case 11: e = CV_LAUNCH(2, true, true); break;
+    // TMA ring (plan-order blocks or whole small frames) unless the plan gathers from the caller's frames
+    const bool pipe = hp.mode != CV_MODE_DIRECT;
+#define CV_LAUNCH(B, P_) (lean ? launch_features<B, P_, true>(plan, rp, st) : launch_features<B, P_, false>(plan, rp, st))
+    switch (hp.desc.box_kind * 2 + (pipe ? 1 : 0)) {
+        case 0: e = CV_LAUNCH(0, false); break;
+        case 1: e = CV_LAUNCH(0, true); break;
+        case 2: e = CV_LAUNCH(1, false); break;
+        case 3: e = CV_LAUNCH(1, true); break;
+        case 4: e = CV_LAUNCH(2, false); break;
+        case 5: e = CV_LAUNCH(2, true); break;
         default: return fail(CV_E_INVALID, "internal: no kernel flavour for this plan");
     }
 #undef CV_LAUNCH
@@ -489,19 +471,39 @@ extern "C" int caviar_weighted_scores(const CvPlan* plan, const uint32_t* flags_
 // Block loop with two device buffer sets: while block b computes, block b+1 is uploaded and block b-1 is
 // downloaded.  Pageable host memory goes through pinned bounce buffers (one memcpy each way); memory the
 // caller pinned (cudaHostAlloc / cudaHostRegister / torch pin_memory) is DMA'd in place.
+namespace {
+// the *_host entry points select the plan's device for their own calls and hand the caller's device back on return
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t enter(int dev) {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) { prev = -1; return e; }
+        return prev == dev ? cudaSuccess : cudaSetDevice(dev);
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+}  // namespace
+
 extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, int64_t frame_stride_floats,
                                     const float* box_host, int64_t n_frames, const CvHostOutputs* out,
-                                    int64_t frames_per_block) {
+                                    int64_t frames_per_block, int32_t input_order) {
     g_launches = 0;
     if (!plan || !out) return fail(CV_E_INVALID, "null argument");
     if (n_frames < 0) return fail(CV_E_INVALID, "negative frame count");
     const HostPlan& hp = plan->hp;
+    if (input_order != CV_ORDER_CALLER && input_order != CV_ORDER_PLAN) return fail(CV_E_INVALID, "unknown input_order");
+    // frames already sliced in plan order (caviar_plan_atom_order): nothing to permute on the device
+    const bool plan_order = input_order == CV_ORDER_PLAN && hp.mode == CV_MODE_STAGED;
+    const int64_t min_stride = plan_order ? hp.staged_floats : 3ll * hp.desc.n_atoms;
     const int64_t P = hp.P, A = hp.A, W = hp.W, F = P + A;
     const int box_kind = hp.desc.box_kind;
     const int box_floats = box_kind == CV_BOX_ORTHO ? 3 : (box_kind == CV_BOX_TRICLINIC ? 9 : 0);
     if (n_frames > 0 && !xyz_host) return fail(CV_E_INVALID, "null coordinates");
     if (box_kind != CV_BOX_NONE && n_frames > 0 && !box_host) return fail(CV_E_INVALID, "plan has a box but box_host is null");
-    if (frame_stride_floats < 3ll * hp.desc.n_atoms) return fail(CV_E_INVALID, "frame stride smaller than 3*n_atoms");
+    if (frame_stride_floats < min_stride)
+        return fail(CV_E_INVALID, plan_order ? "frame stride smaller than the plan-order frame (staged_floats_per_frame)"
+                                             : "frame stride smaller than 3*n_atoms");
+    if (plan_order && frame_stride_floats % 4 != 0) return fail(CV_E_INVALID, "plan-order frames must be a multiple of 16 bytes apart");
     const bool want_agg = out->occupancy || out->sum || out->sumsq;
     const bool want_moments = out->sum || out->sumsq;
     if (want_agg && (!out->occupancy || (want_moments && !(out->sum && out->sumsq))))
@@ -509,7 +511,8 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
     const bool want_ws = out->score_q32 != nullptr;
     if (want_ws && !out->weights_q32) return fail(CV_E_INVALID, "score_q32 needs weights_q32");
     const bool need_flags = out->flags || want_ws;          // the weighted scores are computed from the flag words
-    CV_CUDA(cudaSetDevice(plan->device));
+    DeviceGuard guard;
+    CV_CUDA(guard.enter(plan->device));
 
     // block size: ~256 MB of input + output per buffer set
     const int64_t in_row = frame_stride_floats * 4 + box_floats * 4;
@@ -531,7 +534,7 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
     CV_CUDA(ws.alloc((size_t)kQueueBytes + (size_t)hp.max_chunks * F * 24));
     for (Set& s : set) {
         CV_CUDA(s.xyz.alloc((size_t)TB * frame_stride_floats * 4));
-        CV_CUDA(s.staged.alloc(hp.mode == CV_MODE_STAGED ? (size_t)TB * hp.staged_floats * 4 : 0));
+        CV_CUDA(s.staged.alloc(hp.mode == CV_MODE_STAGED && !plan_order ? (size_t)TB * hp.staged_floats * 4 : 0));
         CV_CUDA(s.dist.alloc(out->dist ? (size_t)TB * P * 4 : 0));
         CV_CUDA(s.angle.alloc(out->angle ? (size_t)TB * A * 4 : 0));
         CV_CUDA(s.flags.alloc(need_flags ? (size_t)TB * W * 4 : 0));
@@ -615,9 +618,8 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
         // compute
         CV_CUDA(cudaStreamWaitEvent(s_run.s, s.uploaded.e, 0));
         const float* coords = s.xyz.as<float>();
-        if (hp.mode == CV_MODE_STAGED) {
-            rc = caviar_stage_frames(plan, s.xyz.as<float>(), frame_stride_floats, n, s.staged.as<float>(),
-                                     box_floats ? rec_all.as<float>() + t0 * kRecFloats : nullptr, s_run.s);
+        if (hp.mode == CV_MODE_STAGED && !plan_order) {
+            rc = caviar_stage_frames(plan, s.xyz.as<float>(), frame_stride_floats, n, s.staged.as<float>(), s_run.s);
             if (rc != CV_OK) return rc;
             launches += g_launches;
             coords = s.staged.as<float>();
@@ -625,7 +627,8 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
         CvFrameOutputs fo{out->dist ? s.dist.as<float>() : nullptr, out->angle ? s.angle.as<float>() : nullptr,
                           need_flags ? s.flags.as<uint32_t>() : nullptr, out->score ? s.score.as<int32_t>() : nullptr};
         CvAggregates ag{occ.as<uint64_t>(), dev_moments ? sum.as<double>() : nullptr, dev_moments ? sq.as<double>() : nullptr};
-        rc = caviar_run(plan, coords, frame_stride_floats, box_floats ? rec_all.as<float>() + t0 * kRecFloats : nullptr, n, &fo, want_agg ? &ag : nullptr, ws.p, s_run.s);
+        const int64_t run_stride = (hp.mode == CV_MODE_STAGED && !plan_order) ? hp.staged_floats : frame_stride_floats;
+        rc = caviar_run(plan, coords, run_stride, box_floats ? rec_all.as<float>() + t0 * kRecFloats : nullptr, n, &fo, want_agg ? &ag : nullptr, ws.p, s_run.s);
         if (rc != CV_OK) return rc;
         launches += g_launches;
         if (want_ws) {
@@ -663,10 +666,6 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
     }
     CV_CUDA(cudaStreamSynchronize(s_run.s));
     quiesce.armed = false;
-    if (hp.mode == CV_MODE_STAGED && box_floats && hp.frac_begin < hp.staged_floats) {
-        int rc = caviar_plan_status(plan, s_run.s);
-        if (rc != CV_OK) return rc;
-    }
     g_launches = launches;
     return CV_OK;
 }
@@ -723,7 +722,7 @@ extern "C" int caviar_pair_distances_host(const float* xyz_host, int64_t n_frame
     tr.mark(hit ? "pair_distances: cached plan" : "pair_distances: plan_create");
     CvHostOutputs o{};
     o.dist = dist_host;
-    int rc = caviar_features_host(oc.plan, xyz_host, 3ll * n_atoms, nullptr, n_frames, &o, 0);
+    int rc = caviar_features_host(oc.plan, xyz_host, 3ll * n_atoms, nullptr, n_frames, &o, 0, CV_ORDER_CALLER);
     tr.mark("pair_distances: features_host");
     return rc;
 }
@@ -846,16 +845,20 @@ inline char* put_u64(char* p, unsigned long long v) {
     return p;
 }
 // "%.{dec}f" of a float.  (double)v * 10^dec is exact for dec <= 8 (24 + 27 bits < 53), and nearbyint() rounds
-// half-to-even exactly like printf does on the exact binary value.
+// half-to-even exactly like printf does on the exact binary value.  Values whose scaled magnitude does not fit 64 bits
+// (and non-finite ones) go through snprintf; kFixedChars bounds what either path can write.
+constexpr int kFixedChars = 64;       // sign + 39 integer digits of FLT_MAX + '.' + 17 decimals, rounded up
 inline char* put_fixed(char* p, float v, int dec, double scale) {
-    if (!(std::fabs(v) < 1e15f) || dec > 8) return p + snprintf(p, 48, "%.*f", dec, (double)v);
-    double x = std::nearbyint(std::fabs((double)v) * scale);
-    unsigned long long q = (unsigned long long)x;
-    if (std::signbit(v) && q != 0) *p++ = '-';
-    else if (std::signbit(v) && q == 0) *p++ = '-';      // printf prints "-0.0000" for small negatives as well
-    unsigned long long ip = q, fp = 0, pw = 1;
+    const double mag = std::fabs((double)v) * scale;
+    if (!(mag < 1.8e19) || dec > 8) {
+        const int n = snprintf(p, kFixedChars, "%.*f", dec, (double)v);
+        return p + std::min(std::max(n, 0), kFixedChars - 1);
+    }
+    const unsigned long long q = (unsigned long long)std::nearbyint(mag);
+    if (std::signbit(v)) *p++ = '-';                     // printf prints "-0.0000" for small negatives as well
+    unsigned long long pw = 1;
     for (int i = 0; i < dec; ++i) pw *= 10;
-    ip = q / pw; fp = q % pw;
+    const unsigned long long ip = q / pw, fp = q % pw;
     p = put_u64(p, ip);
     if (dec > 0) {
         *p++ = '.';
@@ -866,30 +869,37 @@ inline char* put_fixed(char* p, float v, int dec, double scale) {
 }  // namespace
 
 extern "C" int64_t caviar_format_csv(const float* values, int64_t rows, int64_t cols, int64_t row_stride_floats,
-                                     int64_t first_index, int64_t index_step, int32_t decimals, char* out, int64_t cap) {
+                                     int64_t first_index, int64_t index_step, int32_t decimals, int32_t crlf,
+                                     char* out, int64_t cap) {
     if (rows < 0 || cols < 0 || decimals < 0 || decimals > 17) return fail(CV_E_INVALID, "bad csv shape");
     if (rows == 0) return 0;
     if (!values || !out) return fail(CV_E_INVALID, "null argument");
-    const int64_t per_row = 24 + 48 * cols;                    // worst case of one row
+    const int64_t per_row = 24 + (int64_t)(kFixedChars + 1) * cols;     // worst case of one row
     const double scale = std::pow(10.0, decimals);
     unsigned hw = std::thread::hardware_concurrency();
     int nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(hw ? hw : 4, 32), rows * cols / 65536 + 1));
-    std::vector<std::string> parts(nt);
+    // per-thread buffers grow geometrically from an estimate of the typical row (a few integer digits + the decimals);
+    // only the worst case of ONE row is ever reserved ahead of the cursor
+    struct Part { std::vector<char> buf; size_t len = 0; size_t size() const { return len; } const char* data() const { return buf.data(); } };
+    std::vector<Part> parts(nt);
     std::vector<std::thread> pool;
+    const int64_t typical_row = 12 + (int64_t)(decimals + 8) * cols;
     auto work = [&](int k) {
         const int64_t r0 = rows * k / nt, r1 = rows * (k + 1) / nt;
-        std::string& buf = parts[k];
-        buf.resize((size_t)((r1 - r0) * per_row));
-        char* p = &buf[0];
+        Part& part = parts[k];
+        part.buf.resize((size_t)((r1 - r0) * typical_row + per_row));
         for (int64_t r = r0; r < r1; ++r) {
+            if (part.len + (size_t)per_row > part.buf.size()) part.buf.resize(part.buf.size() + part.buf.size() / 2 + (size_t)per_row);
+            char* p = part.buf.data() + part.len;
             long long idx = first_index + r * index_step;
             if (idx < 0) { *p++ = '-'; idx = -idx; }
             p = put_u64(p, (unsigned long long)idx);
             const float* row = values + r * row_stride_floats;
             for (int64_t c = 0; c < cols; ++c) { *p++ = ','; p = put_fixed(p, row[c], decimals, scale); }
+            if (crlf) *p++ = '\r';                               // csv.writer's line terminator (Extractor:196-198)
             *p++ = '\n';
+            part.len = (size_t)(p - part.buf.data());
         }
-        buf.resize((size_t)(p - &buf[0]));
     };
     for (int k = 1; k < nt; ++k) pool.emplace_back(work, k);
     work(0);

@@ -11,19 +11,12 @@ constexpr int kTileWidth       = kConsumerThreads * kFeatPerThread;   // 896 fea
 constexpr int kMaxShifts       = 16;    // lattice translations the image search may have to try
 constexpr int kRecFloats       = 12 + 4 * kMaxShifts + kMaxShifts + 12;  // 104 floats = 416 B per frame
 constexpr int kMaxStages       = 8;
-// Periodic staged plans keep the blocks of their TRIPLET tiles as 32-bit fixed-point fractional coordinates.
-// CV_FRAC_PAIRS=1 does the same for the pair blocks (parity-green as well, same speed for orthorhombic cells, but
-// 2.5 % slower on config 3: long-range pairs of a triclinic cell still need the float32 reduce + search afterwards);
-// the default keeps pair blocks in float32, wrapped into the unit cell by K0.
-#ifndef CV_FRAC_PAIRS
-#define CV_FRAC_PAIRS 0
-#endif
-constexpr bool kFracPairs = CV_FRAC_PAIRS != 0;
 
 // box record layout (floats)
 enum : int {
     REC_AX = 0, REC_BY = 1, REC_CZ = 2, REC_BX = 3, REC_CX = 4, REC_CY = 5,
-    REC_IAX = 6, REC_IBY = 7, REC_ICZ = 8, REC_RSAFE2 = 9, REC_NSHIFT = 10, REC_PAD = 11,
+    REC_IAX = 6, REC_IBY = 7, REC_ICZ = 8, REC_RSAFE2 = 9, REC_NSHIFT = 10,
+    REC_FAR = 11,                          // |component| of a raw displacement beyond which it is pre-reduced in fp64
     REC_SHIFTS = 12,                       // kMaxShifts x float4 {vx, vy, vz, |v|^2 / 2}
     REC_COEF = REC_SHIFTS + 4 * kMaxShifts,  // kMaxShifts x int: (sa+2) | (sb+2)<<4 | (sc+2)<<8, v = sa*a + sb*b + sc*c
     REC_DBL = REC_COEF + kMaxShifts        // 6 doubles: ax, by, cz, bx, cx, cy (8-byte aligned: 92 floats in)
@@ -43,7 +36,7 @@ struct TileDesc {
 };
 
 struct RunParams {
-    const float* coords;        // staged buffer, or the caller's frames
+    const float* coords;        // plan-order frames (staged layout), or the caller's frames
     long long    frame_stride;  // floats between consecutive frames of `coords`
     const float* boxrec;        // kRecFloats per frame, or nullptr
     long long    n_frames;

@@ -1,10 +1,11 @@
 // Host-side planning for the CAVIAR pair-feature path (pure C++, no CUDA calls).
 //
 // A plan cuts the feature list (pairs first, then triplets; column order = input order, CAVIAR-1.0.py:122)
-// into column tiles of <= 896 features, decides how coordinates reach the SMs (per-tile staged blocks streamed by
-// TMA / one shared block or the caller's frame streamed whole / gathers from global memory for large overlapping
-// selections), lays out the staged blocks (bank-conflict-free atom order, fixed-point blocks of periodic triplet
-// tiles) and sizes the TMA ring and the work queue.  (tile, frame chunk) work items are handed to the persistent
+// into column tiles of <= 896 features, decides how coordinates reach the SMs (per-tile blocks of raw float32 xyz in
+// PLAN ORDER streamed by TMA / one shared block or the caller's frame streamed whole / gathers from global memory for
+// large overlapping selections), lays out the plan order (bank-conflict-free atom order inside every block) and sizes
+// the TMA ring and the work queue.  The plan order is published (src_off / caviar_plan_atom_order) so that whoever
+// slices the atoms out of the trajectory (CAVIAR-1.0.py:335) can hand the frames over in that order.  (tile, frame chunk) work items are handed to the persistent
 // CTAs at run time, so that the atom offsets of a tile stay in registers for a whole item.
 #pragma once
 #include <algorithm>
@@ -31,8 +32,6 @@ struct HostPlan {
     std::vector<int32_t> idx0, idx1, idx2;
     std::vector<int32_t> src_off;      // staged float j of a frame <- float src_off[j] of the input frame
     int64_t staged_floats = 0;
-    bool gather_global = false;        // staged, but the kernel gathers with LDG from the compact staged frame (no TMA ring)
-    int64_t frac_begin = 0;            // staged floats [frac_begin, staged_floats) are fixed-point fractional coordinates
     int64_t n_distinct = 0;
     int64_t bank_conflict_refs = 0;    // gather references left on an already-used shared-memory bank (staged mode)
     int frames_per_stage = 1, n_stages = 0, stage_floats = 0, smem_bytes = 0, whole_frame = 0;
@@ -206,8 +205,8 @@ inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
     // compacted selection, TMA-streamed whole while it is small.  (3) Beyond ~16 KB the whole-block refill per tile
     // and frame costs more than it saves (measured: all pairs of 3 000 / 5 000 atoms run 1.3x / 1.9x faster gathered
     // with LDG through L1/L2 than through a 36 / 60 KB whole-frame ring), so large overlapping selections are
-    // gathered from global memory: from the caller's frames without a box, from K0's compact wrapped / fixed-point
-    // frame with one (hp.gather_global).  Per-tile blocks for such lists would multiply the frame thousands of times.
+    // gathered from the caller's frames in global memory.  Per-tile blocks for such lists would multiply the frame
+    // thousands of times.
     const int64_t frame_bytes = 12ll * d.n_atoms;
     const int64_t u_pad_all = (hp.n_distinct + 3) / 4 * 4;
     constexpr int64_t kWholeBlockBytes = 16 * 1024;
@@ -217,23 +216,19 @@ inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
     // per-tile blocks would multiply the input bytes by more than ~8 (moderate sharing, e.g. random lists over few
     // atoms, is better served by per-tile blocks than by uncoalesced LDG gathers: 7x faster on config 3)
     const bool blow_up = sum_u > 8 * (hp.n_distinct + 1024);
-    const bool one_kind_block = !(periodic && hp.A > 0 && !kFracPairs);   // float pair atoms and fixed-point triplet atoms cannot share
-    const bool zc_ok = !periodic && (d.n_atoms % 4 == 0) && frame_bytes <= (C <= 2 ? 48 * 1024 : kWholeBlockBytes);
+    const bool zc_ok = (d.n_atoms % 4 == 0) && frame_bytes <= (C <= 2 ? 48 * 1024 : kWholeBlockBytes);
     bool shared_group = false;
-    hp.gather_global = false;
     if (d.flags & CV_PLAN_FORCE_DIRECT) {
         hp.mode = CV_MODE_DIRECT;
     } else if (d.flags & CV_PLAN_FORCE_STAGED) {
         hp.mode = CV_MODE_STAGED;
-        shared_group = heavy && small_all && one_kind_block;
+        shared_group = heavy && small_all;
     } else if (zc_ok && ((int64_t)C * d.n_atoms <= 2 * sum_u + 1024 || (heavy && 4 * hp.n_distinct >= 3ll * d.n_atoms))) {
         hp.mode = CV_MODE_ZEROCOPY;          // tiles need most of the (small) frame anyway: stream it as it is
-    } else if (heavy && small_all && one_kind_block) {
+    } else if (heavy && small_all) {
         hp.mode = CV_MODE_STAGED; shared_group = true;
-    } else if (blow_up && !periodic) {
-        hp.mode = CV_MODE_DIRECT;
     } else if (blow_up) {
-        hp.mode = CV_MODE_STAGED; hp.gather_global = true;
+        hp.mode = CV_MODE_DIRECT;
     } else {
         hp.mode = CV_MODE_STAGED;
     }
@@ -243,24 +238,7 @@ inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
     hp.idx1.assign((size_t)C * kTileWidth, 0);
     hp.idx2.assign((size_t)C * kTileWidth, 0);
     hp.src_off.clear();
-    std::vector<int32_t> global_slot, pair_slot, trip_slot;
-    int32_t trip_block_off = 0, pair_block_floats = 0, trip_block_floats = 0;
-    if (hp.gather_global) {
-        // one compact block per kind: [atoms of the pair tiles][atoms of the triplet tiles], each sorted by atom index
-        auto compact = [&](const std::vector<int32_t>& refs, std::vector<int32_t>& slot) -> int32_t {
-            std::vector<uint8_t> used((size_t)d.n_atoms, 0);
-            for (int32_t v : refs) used[v] = 1;
-            slot.assign((size_t)d.n_atoms, -1);
-            int32_t k = 0, last = -1;
-            for (int32_t a = 0; a < d.n_atoms; ++a)
-                if (used[a]) { slot[a] = k++; last = a; hp.src_off.insert(hp.src_off.end(), {3 * a, 3 * a + 1, 3 * a + 2}); }
-            for (; last >= 0 && k % 4 != 0; ++k) hp.src_off.insert(hp.src_off.end(), {3 * last, 3 * last + 1, 3 * last + 2});
-            return 3 * k;
-        };
-        pair_block_floats = compact(hp.pairs, pair_slot);
-        trip_block_off = pair_block_floats;
-        trip_block_floats = compact(hp.triplets, trip_slot);
-    }
+    std::vector<int32_t> global_slot;
     if (hp.mode == CV_MODE_STAGED && shared_group) {
         global_slot.assign((size_t)d.n_atoms, -1);
         int32_t k = 0, last = 0;
@@ -270,7 +248,6 @@ inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
     }
     int max_grp_floats = 0;
     hp.bank_conflict_refs = 0;
-    hp.frac_begin = -1;
     std::vector<int32_t> slot_of;      // per-tile: slot of ua[i] inside the tile's staged block
     for (int c = 0; c < C; ++c) {
         TileDesc& t = hp.tiles[c];
@@ -278,23 +255,10 @@ inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
         auto rank = [&](int32_t atom) -> int32_t { return (int32_t)(std::lower_bound(ua.begin(), ua.end(), atom) - ua.begin()); };
         auto local = [&](int32_t atom) -> int32_t {
             if (hp.mode != CV_MODE_STAGED) return 3 * atom;
-            if (hp.gather_global) return 3 * (t.kind == KIND_PAIR ? pair_slot[atom] : trip_slot[atom]);
             if (shared_group) return 3 * global_slot[atom];
             return 3 * slot_of[rank(atom)];
         };
-        if (hp.gather_global) {
-            const bool trip = t.kind == KIND_TRIPLET;
-            t.grp_off = trip ? trip_block_off : 0;
-            t.grp_floats = trip ? trip_block_floats : pair_block_floats;
-            if (trip || kFracPairs) {
-                t.reserved[0] = 1;
-                if (hp.frac_begin < 0) hp.frac_begin = kFracPairs ? 0 : trip_block_off;
-            }
-        } else if (hp.mode == CV_MODE_STAGED && !shared_group) {
-            if ((t.kind == KIND_TRIPLET || kFracPairs) && d.box_kind != CV_BOX_NONE) {
-                t.reserved[0] = 1;                                    // fractional fixed-point block
-                if (hp.frac_begin < 0) hp.frac_begin = (int64_t)hp.src_off.size();
-            }
+        if (hp.mode == CV_MODE_STAGED && !shared_group) {
             int n_slots = 0;
             hp.bank_conflict_refs += assign_bank_slots(hp, t, ua, slot_of, n_slots);
             const int u_pad = round_up(n_slots, 4);
@@ -324,12 +288,10 @@ inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
         }
     }
     hp.staged_floats = (hp.mode == CV_MODE_STAGED) ? (int64_t)hp.src_off.size() : 0;
-    if (hp.mode == CV_MODE_STAGED && shared_group && d.box_kind != CV_BOX_NONE && kFracPairs) hp.frac_begin = 0;
-    if (hp.frac_begin < 0 || hp.mode != CV_MODE_STAGED) hp.frac_begin = hp.staged_floats;   // triplet tiles come last
     hp.whole_frame = (hp.mode == CV_MODE_ZEROCOPY) || (hp.mode == CV_MODE_STAGED && shared_group);
 
     // ---- pipeline geometry ----
-    if (hp.mode == CV_MODE_DIRECT || hp.gather_global) {
+    if (hp.mode == CV_MODE_DIRECT) {
         hp.frames_per_stage = 1; hp.n_stages = 0; hp.stage_floats = 0; hp.smem_bytes = 0; hp.occupancy = 2;
     } else {
         const int gb = max_grp_floats * 4;
@@ -372,7 +334,7 @@ inline void fill_info(const HostPlan& hp, CvPlanInfo& info) {
     info.mode = hp.mode;
     info.n_tiles = (int)hp.tiles.size();
     info.n_ctas = hp.n_ctas;
-    info.threads_per_cta = kConsumerThreads + ((hp.mode == CV_MODE_DIRECT || hp.gather_global) ? 0 : kProducerThreads);
+    info.threads_per_cta = kConsumerThreads + ((hp.mode == CV_MODE_DIRECT) ? 0 : kProducerThreads);
     info.stages = hp.n_stages;
     info.frames_per_stage = hp.frames_per_stage;
     info.smem_bytes = hp.smem_bytes;
@@ -385,7 +347,7 @@ inline void fill_info(const HostPlan& hp, CvPlanInfo& info) {
     info.workspace_bytes = kQueueBytes + (int64_t)hp.max_chunks * (hp.P + hp.A) * 24;
     const int64_t box_b = hp.desc.box_kind == CV_BOX_NONE ? 0 : (hp.desc.box_kind == CV_BOX_ORTHO ? 12 : 36);
     info.gather_bank_conflicts = hp.bank_conflict_refs;
-    info.staged_fixedpoint_floats = hp.staged_floats - hp.frac_begin;
+    info.staged_fixedpoint_floats = 0;       // (ABI 2 field) the staged layout is raw float32 throughout
     info.algorithmic_bytes_per_frame = 12 * hp.n_distinct + box_b + 4 * hp.P + 4 * hp.A + 4 * hp.W + 4;
 }
 

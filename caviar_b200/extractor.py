@@ -121,13 +121,21 @@ def select_atoms(top, labels: Sequence[PairLabel], numbering: str, offset: int) 
     return out
 
 
-def format_rows(values: np.ndarray, first_index: int, step: int, decimals: int) -> bytes:
-    """``index,v,v,...`` lines through the native formatter (caviar_format_csv)."""
+def format_rows(values: np.ndarray, first_index: int, step: int, decimals: int, crlf: bool = True) -> bytes:
+    """``index,v,v,...`` lines through the native formatter (caviar_format_csv).  Lines end in CR LF by default: the
+    reference writes its rows through ``csv.writer`` (CAVIAR_Distances-Extractor.py:196-198), whose line terminator
+    that is."""
     from . import _lib
     values = np.ascontiguousarray(values, dtype=np.float32)
     rows, cols = values.shape
-    buf = np.empty(int(rows * (24 + 48 * cols)) + 16, dtype=np.uint8)      # worst case; not zero-filled, not copied
-    n = _lib.lib.caviar_format_csv(values.ctypes.data, rows, cols, cols, first_index, step, decimals, buf.ctypes.data, buf.size)
+    # ordinary magnitudes (< 1e9) take at most 12 + decimals bytes per value; rows with wilder numbers make the
+    # formatter answer CV_E_NOMEM and the call is repeated with the worst-case capacity (65 bytes per value)
+    for per_value in (13 + int(decimals), 66):
+        buf = np.empty(int(rows * (26 + per_value * cols)) + 16, dtype=np.uint8)   # not zero-filled, not copied
+        n = _lib.lib.caviar_format_csv(values.ctypes.data, rows, cols, cols, first_index, step, decimals, int(bool(crlf)),
+                                       buf.ctypes.data, buf.size)
+        if n != _lib.CV_E_NOMEM:
+            break
     if n < 0:
         _lib.check(int(n))
     return buf[:n].tobytes()
@@ -199,13 +207,18 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     with FeaturePlan(len(used), pairs_c, trip_c if len(triplets) else None, box=box_kind, pair_cutoff=args.cutoff,
                      hbond_dist_cutoff=args.hbond_cutoffs[0], hbond_angle_cutoff=args.hbond_cutoffs[1]) as plan, \
             open(args.out, "wb") as fout:
-        fout.write((",".join(["#Frame"] + colnames) + "\n").encode())
+        # header and rows end in CR LF: the reference writes both through csv.writer (Extractor:196-198)
+        fout.write((",".join(["#Frame"] + colnames) + "\r\n").encode())
+        # the atoms leave the mapped file already in the PLAN's order (per-tile blocks, CAVIAR-1.0.py:335 with the
+        # plan's list): the fused kernel streams those blocks as they are, no permutation pass on the device
+        order = plan.atom_order
+        sel = used if order is None else used[order]
         for b0 in range(0, n_sel, block):
             ids = frame_ids[b0:b0 + block]
             lo, hi = int(ids[0]), int(ids[-1]) + 1
-            xyz = traj.coords_of(used, lo, hi, stride)          # native multi-threaded gather (+ byte order) from the mapped file
+            xyz = traj.coords_of(sel, lo, hi, stride)           # native multi-threaded gather (+ byte order) from the mapped file
             cell = traj.cell(lo, hi, stride) if box_kind else None
-            res = plan.features_host(xyz, cell, want=want, weights=weights)
+            res = plan.features_host(xyz, cell, want=want, weights=weights, plan_order=order is not None)
             fout.write(format_rows(res["dist"], b0 + 1, 1, args.decimals))       # cpptraj's 1-based set index
             if npy is not None:
                 npy[b0:b0 + len(ids)] = res["dist"]

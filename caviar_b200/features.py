@@ -14,7 +14,8 @@ import numpy as np
 
 from . import _lib
 from ._lib import (BOX_NONE, BOX_ORTHO, BOX_TRICLINIC, CvAggregates, CvFrameOutputs, CvHostOutputs, CvPlanDesc,
-                   CvPlanInfo, MODE_DIRECT, MODE_STAGED, MODE_ZEROCOPY, PLAN_FORCE_DIRECT, PLAN_FORCE_STAGED, check)
+                   CvPlanInfo, MODE_DIRECT, MODE_STAGED, MODE_ZEROCOPY, ORDER_CALLER, ORDER_PLAN, PLAN_FORCE_DIRECT,
+                   PLAN_FORCE_STAGED, check)
 
 _BOX_KINDS = {None: BOX_NONE, "none": BOX_NONE, "ortho": BOX_ORTHO, "orthorhombic": BOX_ORTHO,
               "triclinic": BOX_TRICLINIC}
@@ -140,6 +141,8 @@ class FeaturePlan:
             check(_lib.lib.caviar_plan_create(C.byref(desc), C.byref(self._handle)))
             check(_lib.lib.caviar_plan_info(self._handle, C.byref(info)))
         self.info = info.as_dict()
+        # the layout accessors re-run the (deterministic) host planner; the plan order does not depend on the SM count
+        self._sms = int(describe_only_sms) if describe_only_sms is not None else 148
         self.P, self.A = len(self.pairs), len(self.triplets)
         self.F = self.P + self.A
         self.W = int(info.n_flag_words)
@@ -148,7 +151,7 @@ class FeaturePlan:
 
     def layout(self) -> dict:
         """The planner's tables (host-side, no CUDA): ``tiles`` (n_tiles, 8) = kind, f_begin, n_feat, idx_off, grp_off,
-        grp_floats, fixed_point, 0; ``idx`` (3, n_tiles*896) float offsets inside a tile's block; ``src_off`` (S,)."""
+        grp_floats, 0, 0; ``idx`` (3, n_tiles*896) float offsets inside a tile's block; ``src_off`` (S,)."""
         n_tiles, S = int(self.info["n_tiles"]), int(self.info["staged_floats_per_frame"])
         tiles = np.zeros((n_tiles, 8), dtype=np.int32)
         idx = np.zeros((3, n_tiles * 896), dtype=np.int32)
@@ -156,6 +159,25 @@ class FeaturePlan:
         check(_lib.lib.caviar_plan_layout(C.byref(self._desc), int(self._describe_sms or 148), tiles.ctypes.data,
                                           idx.ctypes.data, src.ctypes.data if S else None))
         return {"tiles": tiles, "idx": idx, "src_off": src}
+
+    @property
+    def atom_order(self) -> Optional[np.ndarray]:
+        """The PLAN ORDER: (S/3,) int32, slot k of a plan-order frame holds atom ``atom_order[k]`` of the caller's
+        numbering (per-tile blocks; an atom referenced by several tiles is repeated, block tails are padded).
+        ``frames[:, plan.atom_order, :]`` is the hand-over format of staged plans -- what ``atom_slice(...).xyz``
+        (CAVIAR-1.0.py:335) produces when it is given this list.  ``None`` for plans that are not staged (those read
+        the caller's frames as they are)."""
+        if self.mode != MODE_STAGED:
+            return None
+        if getattr(self, "_atom_order", None) is None:
+            n = int(self.info["staged_floats_per_frame"]) // 3
+            order = np.zeros(n, dtype=np.int32)
+            got = _lib.lib.caviar_plan_atom_order(C.byref(self._desc), int(self._sms), order.ctypes.data, n)
+            if got < 0:
+                check(int(got))
+            assert got == n
+            self._atom_order = order
+        return self._atom_order
 
     # -- lifetime ---------------------------------------------------------------------------------
     def close(self):
@@ -195,11 +217,9 @@ class FeaturePlan:
         return rec
 
     def stage(self, xyz, boxrec=None, out=None):
-        """K0: (T, N, 3) CUDA float32 frames -> staged (T, S) layout.  Identity for non-staged plans.
-
-        A periodic plan needs ``boxrec = prepare_box(box)`` of the same frames: K0 translates atoms into the unit
-        cell and stores the atoms of triplet tiles as fixed-point fractional coordinates
-        (``info["staged_fixedpoint_floats"]``)."""
+        """K0: (T, N, 3) CUDA float32 frames in the caller's atom order -> plan-order (T, S) layout, i.e.
+        ``xyz[:, plan.atom_order, :]`` on the device (bit-for-bit copies).  Identity for non-staged plans.
+        ``boxrec`` is accepted for source compatibility and ignored: staging is pure data movement."""
         import torch
         if self.mode != MODE_STAGED:
             return xyz
@@ -211,16 +231,10 @@ class FeaturePlan:
         S = int(self.info["staged_floats_per_frame"])
         if out is None:
             out = torch.empty((T, S), dtype=torch.float32, device=xyz.device)
-        if boxrec is not None and (boxrec.shape[0] < T or not boxrec.is_contiguous()):
-            raise ValueError("boxrec must hold one contiguous record per staged frame")
         check(_lib.lib.caviar_stage_frames(self._handle, xyz.data_ptr(), xyz.stride(0) if T > 1 else 3 * self.n_atoms,
-                                           T, out.data_ptr(), None if boxrec is None else boxrec.data_ptr(),
-                                           self._stream_ptr()))
+                                           T, out.data_ptr(), self._stream_ptr()))
+        self.last_launches = int(_lib.lib.caviar_last_launch_count())
         return out
-
-    def check(self):
-        """Synchronise the current stream and raise if K0 met a NaN / Inf coordinate it had to stage as fixed point."""
-        check(_lib.lib.caviar_plan_status(self._handle, self._stream_ptr()))
 
     def new_aggregates(self, device="cuda", moments: bool = True) -> Aggregates:
         """Zeroed running aggregates; ``moments=False`` keeps the occupancy only (contact-map runs)."""
@@ -259,9 +273,14 @@ class FeaturePlan:
             raise TypeError("run() wants a CUDA float32 tensor")
         T = coords.shape[0] if n_frames is None else int(n_frames)
         if self.mode == MODE_STAGED:
-            if coords.dim() != 2 or coords.shape[1] != self.info["staged_floats_per_frame"] or not coords.is_contiguous():
-                raise ValueError("staged plan: pass the tensor returned by stage()")
-            stride = coords.shape[1]
+            S = int(self.info["staged_floats_per_frame"])
+            ok = (coords.dim() == 2 and coords.shape[1] == S and coords.stride(1) == 1) or \
+                 (coords.dim() == 3 and coords.shape[1] * 3 == S and coords.shape[2] == 3 and coords.stride(2) == 1
+                  and coords.stride(1) == 3)
+            if not ok:
+                raise ValueError(f"staged plan: pass frames in plan order -- (T, {S // 3}, 3) = frames[:, plan.atom_order, :], "
+                                 "or the (T, S) tensor returned by stage()")
+            stride = coords.stride(0) if coords.shape[0] > 1 else S
         else:
             if coords.dim() != 3 or coords.shape[1] != self.n_atoms or coords.shape[2] != 3 \
                     or coords.stride(2) != 1 or coords.stride(1) != 3:
@@ -307,14 +326,18 @@ class FeaturePlan:
 
     # -- reference-facing host path ---------------------------------------------------------------
     def features_host(self, xyz: np.ndarray, box=None, want: Sequence[str] = ("dist", "angle", "flags", "score", "agg"),
-                      frames_per_block: int = 0, out: Optional[dict] = None, weights=None) -> dict:
-        """HOST arrays in, HOST arrays out (H2D, kernels, D2H inside).  ``xyz`` is (T, N, 3) float32.
+                      frames_per_block: int = 0, out: Optional[dict] = None, weights=None, plan_order: bool = False) -> dict:
+        """HOST arrays in, HOST arrays out (H2D, kernels, D2H inside).  ``xyz`` is (T, N, 3) float32 in the caller's atom
+        order, or -- ``plan_order=True``, staged plans -- (T, len(plan.atom_order), 3) already sliced in plan order
+        (``frames[:, plan.atom_order, :]``), which skips the device-side permutation.
 
         ``weights`` (one per feature, pairs first) adds ``res["score_weighted"]``: float64 (T,), the per-frame sum of
         the weights of the set flags (exact 32.32 fixed-point sum on the device, see ``weighted_scores``)."""
         xyz = np.asarray(xyz)
-        if xyz.ndim != 3 or xyz.shape[1] != self.n_atoms or xyz.shape[2] != 3:
-            raise ValueError(f"coordinates must be (T, {self.n_atoms}, 3), got {xyz.shape}")
+        plan_order = bool(plan_order) and self.mode == MODE_STAGED
+        n_in = int(self.info["staged_floats_per_frame"]) // 3 if plan_order else self.n_atoms
+        if xyz.ndim != 3 or xyz.shape[1] != n_in or xyz.shape[2] != 3:
+            raise ValueError(f"coordinates must be (T, {n_in}, 3), got {xyz.shape}")
         xyz = np.ascontiguousarray(xyz, dtype=np.float32)
         T = xyz.shape[0]
         b = normalize_box(box, T, self.box_kind)
@@ -339,15 +362,28 @@ class FeaturePlan:
             wq = quantize_weights(weights, self.F)
             sq = np.empty((T,), dtype=np.int64)
             ho.weights_q32, ho.score_q32 = wq.ctypes.data, sq.ctypes.data
+        shapes = {"dist": ((T, self.P), 4), "angle": ((T, self.A), 4), "flags": ((T, self.W), 4), "score": ((T,), 4),
+                  "occupancy": ((self.F,), 8), "sum": ((self.F,), 8), "sumsq": ((self.F,), 8)}
+        kinds = {"dist": "f", "angle": "f", "flags": "iu", "score": "i", "occupancy": "iu", "sum": "f", "sumsq": "f"}
         for name in ("dist", "angle", "flags", "score", "occupancy", "sum", "sumsq"):
             arr = res.get(name)
             if arr is not None:
+                # raw pointers cross the ABI: a caller-supplied array of the wrong shape / dtype would be overrun
+                shape, item = shapes[name]
                 if isinstance(arr, np.ndarray):
-                    setattr(ho, name, arr.ctypes.data)
-                else:                               # a pinned torch CPU tensor
-                    setattr(ho, name, arr.data_ptr())
-        check(_lib.lib.caviar_features_host(self._handle, xyz.ctypes.data, 3 * self.n_atoms,
-                                            None if b is None else b.ctypes.data, T, C.byref(ho), int(frames_per_block)))
+                    ok = arr.shape == shape and arr.dtype.itemsize == item and arr.dtype.kind in kinds[name] and arr.flags.c_contiguous
+                    ptr = arr.ctypes.data
+                else:                               # a (pinned) torch CPU tensor
+                    ok = tuple(arr.shape) == shape and arr.element_size() == item and arr.is_contiguous() and not arr.is_cuda \
+                        and (arr.dtype.is_floating_point == (kinds[name] == "f"))
+                    ptr = arr.data_ptr()
+                if not ok:
+                    raise ValueError(f"output '{name}' must be a C-contiguous host array of shape {shape} with {item}-byte "
+                                     f"{'float' if kinds[name] == 'f' else 'integer'} items")
+                setattr(ho, name, ptr)
+        check(_lib.lib.caviar_features_host(self._handle, xyz.ctypes.data, 3 * n_in,
+                                            None if b is None else b.ctypes.data, T, C.byref(ho), int(frames_per_block),
+                                            ORDER_PLAN if plan_order else ORDER_CALLER))
         self.last_launches = int(_lib.lib.caviar_last_launch_count())
         if sq is not None:
             res["score_weighted"] = sq.astype(np.float64) / 4294967296.0

@@ -19,8 +19,12 @@
  *   caviar_run (aggregates)      CAVIAR-1.0.py:342,380,496,674,783 (per-pair
  *                                mean over frames = sum/T), :539-545 (mean/var
  *                                from sum, sum of squares), :186 (threshold).
- *   caviar_stage_frames          CAVIAR-1.0.py:335-336,670  atom_slice(ca).xyz
- *                                (the compaction of selected atoms, on the device).
+ *   caviar_plan_atom_order /     CAVIAR-1.0.py:335-336,670  atom_slice(ca).xyz -- the compaction of the selected atoms.
+ *   caviar_stage_frames          The plan publishes the ORDER in which it wants them (per-tile blocks, an atom repeated
+ *                                once per tile that references it); whoever slices the trajectory hands the frames over
+ *                                in that order (raw float32 xyz, nothing else is done to them) and the fused kernel
+ *                                streams them as they are.  caviar_stage_frames is the same permutation on the device
+ *                                for callers whose frames are already compact in their own order.
  *   caviar_compact_frames_host   the same selection at the trajectory-file boundary
  *                                (cpptraj's masks, Extractor:133-138), on the host.
  *   caviar_weighted_scores       north_star extension: per-frame scores weighted by the
@@ -44,7 +48,7 @@
 extern "C" {
 #endif
 
-#define CV_ABI_VERSION 2
+#define CV_ABI_VERSION 3
 
 /* status codes */
 #define CV_OK              0
@@ -67,7 +71,12 @@ extern "C" {
 /* kernel paths a plan can resolve to */
 #define CV_MODE_DIRECT    0    /* gather from global memory, any frame stride */
 #define CV_MODE_ZEROCOPY  1    /* TMA-stream the caller's frames as they are (small, aligned frames) */
-#define CV_MODE_STAGED    2    /* compaction kernel -> grouped layout -> TMA-streamed */
+#define CV_MODE_STAGED    2    /* frames in plan order (per-tile blocks of raw float32 xyz), TMA-streamed */
+
+/* atom order of the frames handed to caviar_features_host */
+#define CV_ORDER_CALLER   0    /* (T, n_atoms, 3) as the pair / triplet lists index it */
+#define CV_ORDER_PLAN     1    /* (T, staged_floats_per_frame / 3, 3): atom caviar_plan_atom_order()[k] in slot k
+                                  (plans whose mode is not CV_MODE_STAGED have no plan order: treated as CALLER) */
 
 typedef struct CvPlan CvPlan;
 
@@ -99,12 +108,11 @@ typedef struct CvPlanInfo {
     int64_t  n_features;              /* P + A */
     int64_t  n_flag_words;            /* ceil(P/32) + ceil(A/32) uint32 words per frame */
     int64_t  n_distinct_atoms;        /* U */
-    int64_t  staged_floats_per_frame; /* floats per frame of the staged layout (0 unless CV_MODE_STAGED) */
+    int64_t  staged_floats_per_frame; /* floats per frame of the plan-order layout (0 unless CV_MODE_STAGED) */
     int64_t  boxrec_floats_per_frame; /* floats per frame of a prepared box record */
     int64_t  workspace_bytes;         /* caller-provided scratch for caviar_run */
     int64_t  algorithmic_bytes_per_frame; /* 12U + box + 4P + 4A + 4*flag_words + 4 */
-    int64_t  staged_fixedpoint_floats; /* trailing part of a staged frame that holds the atoms of the TRIPLET tiles of a
-                                         periodic plan as 32-bit fixed-point fractional coordinates (0 = none) */
+    int64_t  staged_fixedpoint_floats; /* always 0 since ABI 3: plan-order frames are raw float32 xyz throughout */
     int64_t  gather_bank_conflicts;   /* staged mode: gather references the block layout could not keep off a used
                                          shared-memory bank (0 = every warp gather is conflict-free) */
 } CvPlanInfo;
@@ -133,7 +141,7 @@ typedef struct CvAggregates {
 int caviar_plan_describe(const CvPlanDesc* desc, int32_t n_sms, CvPlanInfo* info);
 
 /* Host-side planning only: the layout tables a plan would upload, for CPU-side verification of the planner.
- *   tile_desc [n_tiles][8] int32 = {kind, f_begin, n_feat, idx_off, grp_off, grp_floats, fixed_point, 0}
+ *   tile_desc [n_tiles][8] int32 = {kind, f_begin, n_feat, idx_off, grp_off, grp_floats, 0, 0}
  *   idx       [3][n_tiles*896] int32: float offset (3*slot) of atom role 0/1/2 inside the tile's block
  *   src_off   [staged_floats_per_frame] int32: staged float j <- float src_off[j] of the input frame
  * Any buffer may be NULL. */
@@ -149,23 +157,25 @@ int  caviar_plan_info(const CvPlan* plan, CvPlanInfo* info);
 int caviar_prepare_box(const CvPlan* plan, const float* box_dev, int64_t n_frames,
                        float* boxrec_dev, void* stream);
 
-/* Compaction (CV_MODE_STAGED only): frames (device, frame t at xyz + t*stride
- * floats, AoS xyz) -> staged layout (device, staged_floats_per_frame each).
- * A periodic plan needs the frames' box records (boxrec_dev from caviar_prepare_box, same
- * frames): atoms outside the unit cell are translated into it, and the atoms of triplet
- * tiles are stored as 32-bit fixed-point fractional coordinates
- * (CvPlanInfo.staged_fixedpoint_floats).  Plans without a box take boxrec_dev = NULL. */
-int caviar_stage_frames(const CvPlan* plan, const float* xyz_dev, int64_t frame_stride_floats,
-                        int64_t n_frames, float* staged_dev, const float* boxrec_dev, void* stream);
+/* The plan order (host-side planning only, no CUDA call): slot k of a plan-order frame holds atom order[k] of the
+ * caller's numbering, k in [0, staged_floats_per_frame / 3).  Blocks of consecutive slots belong to one column tile;
+ * an atom referenced by several tiles appears once per tile, block tails are padded with a repeated atom.  Slicing a
+ * trajectory with this list -- frames[:, order, :] -- IS the hand-over format of CV_MODE_STAGED plans (the reference
+ * slices with its own list at CAVIAR-1.0.py:335).  Returns the number of slots (0 for plans that are not staged), or a
+ * negative CV_E_* code; order may be NULL to query the size. */
+int64_t caviar_plan_atom_order(const CvPlanDesc* desc, int32_t n_sms, int32_t* order, int64_t cap);
 
-/* caviar_stage_frames is asynchronous; what it can only find out on the device -- a NaN / Inf coordinate in an atom
- * that is staged as fixed point -- is kept as a sticky flag on the plan.  This call synchronises `stream`, returns
- * CV_E_INVALID if the flag is set, and clears it.  (caviar_features_host checks it itself.) */
-int caviar_plan_status(const CvPlan* plan, void* stream);
+/* The same permutation on the device (CV_MODE_STAGED only): frames (device, frame t at xyz + t*stride floats, AoS xyz,
+ * caller's atom order) -> plan-order layout (device, staged_floats_per_frame each, 16-byte aligned).  Pure data
+ * movement, coordinates are copied bit for bit whatever the box. */
+int caviar_stage_frames(const CvPlan* plan, const float* xyz_dev, int64_t frame_stride_floats,
+                        int64_t n_frames, float* staged_dev, void* stream);
 
 /* The fused hot path over n_frames frames resident on the device.
- *   coords: CV_MODE_STAGED -> the staged buffer; otherwise the frames themselves
+ *   coords: CV_MODE_STAGED -> frames in plan order, raw float32 xyz (frame_stride_floats apart, 0 = densely packed,
+ *           otherwise >= staged_floats_per_frame and a multiple of 4); otherwise the caller's frames themselves
  *           (frame_stride_floats apart; CV_MODE_ZEROCOPY needs stride == 3*n_atoms).
+ *           With a box, atoms may sit anywhere (unwrapped trajectories included): displacements are minimum-imaged.
  *   boxrec: prepared records, NULL iff box_kind == CV_BOX_NONE.
  * Launches on `stream` (a cudaStream_t) and returns without synchronising. */
 int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t frame_stride_floats,
@@ -202,7 +212,7 @@ typedef struct CvHostOutputs {
 
 int caviar_features_host(const CvPlan* plan, const float* xyz_host, int64_t frame_stride_floats,
                          const float* box_host, int64_t n_frames, const CvHostOutputs* out,
-                         int64_t frames_per_block /* 0 = auto */);
+                         int64_t frames_per_block /* 0 = auto */, int32_t input_order /* CV_ORDER_* */);
 
 /* compute_distances_parallel(X, pairs) in one call (no box, no cut-offs): fills dist_host [T][P].
  * CAVIAR-1.0.py:110-122.  The plan and the device / bounce buffers of the LAST call are kept and reused when the
@@ -228,11 +238,14 @@ int caviar_compact_frames_soa_host(const void* src, int64_t n_frames, int64_t fr
 
 /* Host-side CSV row formatter for the Extractor output (CAVIAR_Distances-Extractor.py:147-151,196-198: one frame
  * column, then one distance column per pair).  Formats rows x cols float32 values as
- *     "<first_index + r*index_step>,<v>,<v>,...\n"      with `decimals` fixed decimals (printf "%.Nf" rounding)
- * into `out` (capacity `cap` bytes) using the host cores.  Returns the number of bytes written, or a negative
- * CV_E_* code (CV_E_NOMEM when `cap` is too small: 24 + 28*cols bytes per row always suffice). */
+ *     "<first_index + r*index_step>,<v>,<v>,...<EOL>"    with `decimals` fixed decimals (printf "%.Nf" rounding)
+ * into `out` (capacity `cap` bytes) using the host cores; <EOL> is "\r\n" when crlf != 0 (what Python's csv.writer,
+ * through which the reference writes its rows, emits) and "\n" otherwise.  Returns the number of bytes written, or a
+ * negative CV_E_* code (CV_E_NOMEM when `cap` is too small: 26 + 65*cols bytes per row suffice for any float; rows of
+ * ordinary magnitudes take 3 + digits + decimals bytes per value). */
 int64_t caviar_format_csv(const float* values, int64_t rows, int64_t cols, int64_t row_stride_floats,
-                          int64_t first_index, int64_t index_step, int32_t decimals, char* out, int64_t cap);
+                          int64_t first_index, int64_t index_step, int32_t decimals, int32_t crlf,
+                          char* out, int64_t cap);
 
 /* float64 flavour of compute_distances_parallel: the reference returns float64 when X is float64 (numpy type
  * propagation at CAVIAR-1.0.py:118-119).  Same arithmetic order in IEEE double, bit-exact; HBM-bound gather kernel. */

@@ -23,7 +23,7 @@ def test_header_symbols_all_exported(cb):
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(_lib.lib, name)
-    assert _lib.lib.caviar_abi_version() == 2
+    assert _lib.lib.caviar_abi_version() == 3
 
 
 def test_no_cpu_fallback(cb):
@@ -77,7 +77,7 @@ def test_plan_forced_modes_and_direct(cb):
     # ... of a 12-KB frame: stream the frame as it is
     pairs = rng.integers(0, 1024, size=(5000, 2))
     assert cb.FeaturePlan(1024, pairs, None, describe_only_sms=148).info["mode_name"] == "zerocopy"
-    assert cb.FeaturePlan(1024, pairs, None, box="ortho", describe_only_sms=148).info["mode_name"] == "staged"
+    assert cb.FeaturePlan(1024, pairs, None, box="ortho", describe_only_sms=148).info["mode_name"] == "zerocopy"   # raw floats: a box changes nothing
 
 
 def test_thresholds_match_double_compare():
@@ -130,23 +130,30 @@ def test_staged_blocks_are_bank_conflict_free(cb):
     assert info["gather_bank_conflicts"] >= 0 and info["staged_floats_per_frame"] % 4 == 0
 
 
-def test_periodic_triplet_tiles_are_staged_as_fixed_point(cb):
-    """Periodic plan with triplets: always the staged layout, triplet blocks (the tail of a staged frame) in 32-bit
-    fixed-point fractional coordinates; no box or no triplets: plain float32 blocks."""
+def test_plan_order_is_raw_float_blocks_whatever_the_box(cb):
+    """The staged layout is a pure permutation of the caller's atoms (ABI 3): no fixed-point blocks, the same plan
+    order with and without a box, and small aligned frames are streamed as they are even with a box."""
     rng = np.random.default_rng(8)
     n = 256                                                     # small, aligned frames: zero-copy candidates
     pairs = rng.integers(0, n, size=(4000, 2))
     trips = rng.integers(0, n, size=(500, 3))
-    info = cb.FeaturePlan(n, pairs, trips, box="ortho", describe_only_sms=148).info
-    assert info["mode_name"] == "staged" and info["staged_fixedpoint_floats"] > 0
-    assert info["staged_fixedpoint_floats"] % 12 == 0 and info["staged_fixedpoint_floats"] < info["staged_floats_per_frame"]
-    assert cb.FeaturePlan(n, pairs, trips, box=None, describe_only_sms=148).info["staged_fixedpoint_floats"] == 0
-    only_p = cb.FeaturePlan(n, pairs, None, box="triclinic", describe_only_sms=148).info
-    assert only_p["staged_fixedpoint_floats"] == 0 and only_p["mode_name"] == "staged"     # periodic: never zero-copy
-    assert cb.FeaturePlan(n, pairs, None, box=None, describe_only_sms=148).info["mode_name"] == "zerocopy"
-    only_t = cb.FeaturePlan(n, None, trips, box="triclinic", describe_only_sms=148).info
-    assert only_t["staged_fixedpoint_floats"] == only_t["staged_floats_per_frame"]
-    assert cb.FeaturePlan(n, pairs, trips, box="ortho", force="direct", describe_only_sms=148).info["staged_fixedpoint_floats"] == 0
+    for box in (None, "ortho", "triclinic"):
+        for tr in (None, trips):
+            info = cb.FeaturePlan(n, pairs, tr, box=box, describe_only_sms=148).info
+            assert info["staged_fixedpoint_floats"] == 0 and info["mode_name"] == "zerocopy"
+    n = 5000
+    pairs, trips = rng.integers(0, n, size=(3001, 2)), rng.integers(0, n, size=(700, 3))
+    orders = []
+    for box in (None, "ortho", "triclinic"):
+        plan = cb.FeaturePlan(n, pairs, trips, box=box, describe_only_sms=148)
+        assert plan.info["mode_name"] == "staged" and plan.info["staged_fixedpoint_floats"] == 0
+        order = plan.atom_order
+        assert order.dtype == np.int32 and 3 * len(order) == plan.info["staged_floats_per_frame"] and len(order) % 4 == 0
+        assert np.array_equal(np.unique(order), np.unique(np.concatenate([pairs.ravel(), trips.ravel()])))
+        assert np.array_equal(3 * order, plan.layout()["src_off"][0::3])
+        orders.append(order)
+    assert np.array_equal(orders[0], orders[1]) and np.array_equal(orders[0], orders[2])
+    assert cb.FeaturePlan(n, pairs, None, box=None, force="direct", describe_only_sms=148).atom_order is None
 
 
 def test_large_overlapping_selections_do_not_blow_up_the_staged_layout(cb):
@@ -164,10 +171,9 @@ def test_large_overlapping_selections_do_not_blow_up_the_staged_layout(cb):
     pairs = rows_against_all(5000)
     trips = np.stack([np.arange(0, 300), np.arange(1, 301), np.arange(2, 302)], 1)
     info = cb.FeaturePlan(5000, pairs, trips, box="triclinic", describe_only_sms=148).info
-    assert info["mode_name"] == "staged" and info["stages"] == 0 and info["smem_bytes"] == 0       # LDG from K0's compact frame
-    assert info["staged_floats_per_frame"] <= 3 * (5000 + 304 + 8) and info["staged_fixedpoint_floats"] == 3 * 304
+    assert info["mode_name"] == "direct" and info["stages"] == 0 and info["smem_bytes"] == 0       # LDG from the caller's frames
     info = cb.FeaturePlan(5000, pairs, None, box="ortho", describe_only_sms=148).info
-    assert info["mode_name"] == "staged" and info["staged_floats_per_frame"] <= 3 * 5004     # periodic: compact frame via K0
+    assert info["mode_name"] == "direct" and info["staged_floats_per_frame"] == 0
 
 
 def _check_layout(cb, n, pairs, trips, box, force=None):
@@ -194,8 +200,7 @@ def _check_layout(cb, n, pairs, trips, box, force=None):
             else:
                 atoms = off // 3
             assert np.array_equal(atoms, want[:, role]), (kind, f_begin, role)
-        if staged and box is not None and kind == 1:
-            assert fixed == 1 and grp_off >= len(src) - info["staged_fixedpoint_floats"]
+        assert fixed == 0                                          # ABI 3: raw float32 blocks only
         seen_pairs += n_feat if kind == 0 else 0
         seen_trips += n_feat if kind == 1 else 0
     assert seen_pairs == P and seen_trips == (0 if trips is None else len(trips))
@@ -217,11 +222,11 @@ def test_planner_layout_resolves_every_feature_to_its_atoms(cb):
     assert _check_layout(cb, 61, few, None, None)["mode_name"] == "staged"
     _check_layout(cb, 60, few, rng.integers(0, 60, size=(300, 3)), "triclinic")
     _check_layout(cb, 60, few, None, None, force="staged")
-    # large overlapping selection of a periodic plan: compact per-kind blocks gathered from global memory
+    # large overlapping selection: gathered from the caller's frames in global memory, with or without a box
     rows = np.repeat(np.arange(0, 3000, 50), 3000)
     big = np.stack([rows, np.tile(np.arange(3000), 60)], 1)
     info = _check_layout(cb, 3000, big, rng.integers(0, 3000, size=(100, 3)), "ortho")
-    assert info["mode_name"] == "staged" and info["stages"] == 0
+    assert info["mode_name"] == "direct" and info["stages"] == 0
     assert _check_layout(cb, 3000, big, None, None)["mode_name"] == "direct"
 
 
@@ -240,7 +245,7 @@ def test_plain_c_host_links_against_the_abi(cb, tmp_path):
     subprocess.run([gcc, "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "pair_distances.c"),
                     "-o", exe, "-L", libdir, "-lcaviar_b200", f"-Wl,-rpath,{libdir}"], check=True)
     res = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    assert "ABI version 2" in res.stdout
+    assert "ABI version 3" in res.stdout
     if torch.cuda.is_available():
         assert res.returncode == 0 and "frame 1: 5.0000 20.0000 5.0000" in res.stdout
     else:

@@ -108,14 +108,29 @@ def test_netcdf_roundtrip_and_cell(tmp_path):
 
 
 def test_csv_rows_match_printf(ext):
+    """Rows as Python's csv.writer would write printf-formatted fields (Extractor:196-198): CR LF line ends."""
+    import csv
+    import io
     rng = np.random.default_rng(1)
     v = rng.uniform(0, 300, size=(257, 33)).astype(np.float32)
     v[0, :6] = [0.00005, 0.12345, 0.12355, 7.99995, 0.0, 123456.7]
     got = ext.format_rows(v, 1, 1, 4).decode()
-    want = "".join(f"{r + 1}," + ",".join("%.4f" % float(x) for x in v[r]) + "\n" for r in range(v.shape[0]))
-    assert got == want
-    assert ext.format_rows(v[:2, :2], 5, 3, 2).decode() == "".join(
+    sio = io.StringIO(newline="")
+    csv.writer(sio).writerows([[str(r + 1)] + ["%.4f" % float(x) for x in v[r]] for r in range(v.shape[0])])
+    assert got == sio.getvalue() and got.count("\r\n") == v.shape[0]
+    assert ext.format_rows(v[:2, :2], 5, 3, 2, crlf=False).decode() == "".join(
         f"{5 + 3 * r}," + ",".join("%.2f" % float(x) for x in v[r, :2]) + "\n" for r in range(2))
+
+
+def test_csv_rows_of_any_magnitude(ext):
+    """Values whose scaled magnitude leaves 64 bits, negative zeros, non-finite values: printf's text, no overrun."""
+    v = np.array([[5e11, -5e11, 3e38, -3.4028235e38, 1.8e11, 1.9e11, -0.0, -1e-9, np.inf, -np.inf, np.nan, 1e15, 123.456]],
+                 dtype=np.float32)
+    for dec in (0, 4, 8, 12, 17):
+        got = ext.format_rows(np.repeat(v, 3, axis=0), 7, 2, dec, crlf=False).decode().splitlines()
+        for r, line in enumerate(got):
+            want = f"{7 + 2 * r}," + ",".join("%.*f" % (dec, float(x)) for x in v[0])
+            assert line == want, (dec, line, want)
 
 
 def test_residue_components_match_reference_vectors(meta, golden_dir):

@@ -120,25 +120,41 @@ def test_survey_parity_sets_against_c_oracle(cb, cfg_id, T):
     np.testing.assert_allclose(res["sum"][:P], res["dist"].astype(np.float64).sum(axis=0), rtol=1e-12)
 
 
-def test_fixed_point_staging_needs_box_records(cb):
+def test_plan_order_input_equals_caller_order_input(cb):
+    """The hand-over format of staged plans: frames sliced with plan.atom_order (raw floats, duplicates included) give
+    bit-identical results to the caller-order frames permuted on the device by K0, with and without a box."""
     import torch
     rng = np.random.default_rng(1)
-    n, T = 64, 5
-    x = torch.from_numpy((rng.random((T, n, 3)) * 20).astype(np.float32)).cuda()
-    box = torch.full((T, 3), 20.0, device="cuda")
-    trips = rng.integers(0, n, size=(40, 3))
-    with cb.FeaturePlan(n, [(0, 1)], trips, box="ortho") as plan:
-        assert plan.info["staged_fixedpoint_floats"] > 0
-        with pytest.raises(cb.CaviarError):
-            plan.stage(x)                                       # no box records: refused, not guessed
-        rec = plan.prepare_box(box)
-        out = plan.run(plan.stage(x, rec), rec)
-        want = orc.triplet_angles(x.cpu().numpy(), trips, np.full((T, 3), 20.0))
-        assert np.abs(out.angle.cpu().numpy() - want).max() <= 1e-3
+    n, T = 3000, 9
+    pairs = rng.integers(0, n, size=(2500, 2))
+    trips = rng.integers(0, n, size=(700, 3))
+    x = (rng.random((T, n, 3)) * 20).astype(np.float32)
+    x[:, ::7] += np.float32(60.0)                               # some atoms three cells away
+    for box in (None, "ortho", "triclinic"):
+        cell = {None: None, "ortho": np.full((T, 3), 20.0), "triclinic": np.broadcast_to(orc.box_matrix([20.0] * 3, [109.4712206] * 3), (T, 3, 3)).copy()}[box]
+        with cb.FeaturePlan(n, pairs, trips, box=box) as plan:
+            assert plan.info["mode_name"] == "staged" and plan.info["staged_fixedpoint_floats"] == 0
+            order = plan.atom_order
+            xp = np.ascontiguousarray(x[:, order, :])
+            a = plan.features_host(x, cell)
+            la = plan.last_launches
+            b = plan.features_host(xp, cell, plan_order=True)
+            assert plan.last_launches < la                      # no permutation kernel on the plan-order path
+            for k in ("dist", "angle", "flags", "score", "occupancy", "sum", "sumsq"):
+                assert _bits(a[k]) == _bits(b[k]), (box, k)
+            xd = torch.from_numpy(x).cuda()
+            staged = plan.stage(xd)                             # K0 = the same permutation, bit for bit, box or not
+            assert torch.equal(staged.view(T, -1, 3), torch.from_numpy(xp).cuda())
+            rec = plan.prepare_box(torch.from_numpy(cell.astype(np.float32)).cuda()) if box else None
+            out = plan.run(torch.from_numpy(xp).cuda(), rec)    # (T, S/3, 3) frames in plan order, straight in
+            assert _bits(out.dist.cpu().numpy()) == _bits(a["dist"])
+            with pytest.raises(ValueError):
+                plan.features_host(x, cell, plan_order=True)    # caller-order shape is refused, not guessed
 
 
 def test_unwrapped_coordinates_far_outside_the_cell(cb):
-    """Molecules that diffused many box lengths away (unwrapped trajectories): fractional staging wraps them exactly."""
+    """Molecules that diffused many box lengths away (unwrapped trajectories): displacements that span several cells are
+    re-taken and reduced in fp64 inside the fused kernel (far_displacement)."""
     rng = np.random.default_rng(2)
     n, T, L = 96, 7, 25.0
     base = rng.random((n, 3)) * L
@@ -158,12 +174,11 @@ def test_unwrapped_coordinates_far_outside_the_cell(cb):
 
 
 @pytest.mark.parametrize("n,box,A,mode,stages", [(1000, None, 0, "zerocopy", 2), (3000, None, 0, "direct", 0),
-                                                   (5000, "ortho", 0, "staged", 0), (1000, "triclinic", 64, "staged", 0),
-                                                   (5000, "triclinic", 200, "staged", 0), (9000, None, 0, "direct", 0)])
+                                                   (5000, "ortho", 0, "direct", 0), (1000, "triclinic", 64, "zerocopy", 2),
+                                                   (5000, "triclinic", 200, "direct", 0), (9000, None, 0, "direct", 0)])
 def test_large_overlapping_selection_modes(cb, n, box, A, mode, stages):
     """Rows of a big all-pairs list: per-tile blocks would multiply the frame hundreds of times.  Small frames are
-    streamed whole; large ones are gathered from global memory -- from the caller's frames (no box) or from K0's
-    compact wrapped / fixed-point frame (periodic: mode 'staged' without a TMA ring)."""
+    streamed whole (with or without a box); large ones are gathered from the caller's frames in global memory."""
     from oracle import c_oracle as co
     rng = np.random.default_rng(n + A)
     rows = np.arange(7, n, 211 if n > 1000 else 37)
@@ -198,29 +213,22 @@ def test_large_overlapping_selection_modes(cb, n, box, A, mode, stages):
     assert np.array_equal(res["score"], flags.sum(axis=1).astype(np.int32))
 
 
-def test_non_finite_triplet_coordinates_are_reported(cb):
-    """NaN in, NaN out on the float paths; the fixed-point triplet blocks cannot carry a NaN, so K0 flags it."""
-    import torch
+def test_non_finite_coordinates_propagate(cb):
+    """NaN in, NaN out on every path (plan-order blocks are raw floats: nothing can hide a blown-up frame)."""
     n, T = 32, 4
     rng = np.random.default_rng(3)
     x = (rng.random((T, n, 3)) * 20).astype(np.float32)
     x[2, 5, 1] = np.nan
     box = np.full((T, 3), 20.0)
-    with cb.FeaturePlan(n, [(5, 6), (1, 2)], None, box="ortho") as plan:          # pairs only: NaN propagates
-        d = plan.features_host(x, box, want=("dist",))["dist"]
-        assert np.isnan(d[2, 0]) and np.isfinite(np.delete(d.ravel(), 4)).all()
-    with cb.FeaturePlan(n, [(1, 2)], [(4, 5, 6), (7, 8, 9)], box="ortho") as plan:
-        with pytest.raises(cb.CaviarError, match="non-finite"):
-            plan.features_host(x, box)
-        res = plan.features_host(np.nan_to_num(x), box)                            # the flag was cleared
-        assert np.isfinite(res["angle"]).all()
-        xd = torch.from_numpy(x).cuda()
-        rec = plan.prepare_box(torch.from_numpy(box.astype(np.float32)).cuda())
-        plan.stage(xd, rec)
-        with pytest.raises(cb.CaviarError, match="non-finite"):
-            plan.check()
-        plan.check()                                                                # cleared again
-    with cb.FeaturePlan(n, None, [(4, 5, 6)], box=None) as plan:                   # no box: float path, NaN propagates
+    for force in (None, "staged", "direct"):
+        with cb.FeaturePlan(n, [(5, 6), (1, 2)], None, box="ortho", force=force) as plan:
+            d = plan.features_host(x, box, want=("dist",))["dist"]
+            assert np.isnan(d[2, 0]) and np.isfinite(np.delete(d.ravel(), 4)).all()
+        with cb.FeaturePlan(n, [(1, 2)], [(4, 5, 6), (7, 8, 9)], box="ortho", force=force) as plan:
+            res = plan.features_host(x, box)
+            assert np.isnan(res["angle"][2, 0]) and np.isfinite(np.delete(res["angle"].ravel(), 4)).all()
+            assert np.isfinite(res["dist"]).all()
+    with cb.FeaturePlan(n, None, [(4, 5, 6)], box=None) as plan:
         assert np.isnan(plan.features_host(x, want=("angle",))["angle"][2, 0])
     cb.release_cache()
 
