@@ -111,6 +111,9 @@ def select_atoms(top, labels: Sequence[PairLabel], numbering: str, offset: int) 
                 if res0 >= top.n_res:
                     sys.exit(f"[ERR] residuo {idx} oltre la topologia ({top.n_res} residui) per {ra}{na}-{rb}{nb}")
             else:
+                if top.res_seq is None:
+                    sys.exit("[ERR] --numbering resSeq richiede una topologia con numerazione PDB (pdb/psf/gro); "
+                             "con un prmtop usare --numbering sequential e --offset")
                 res0 = top.residue_by_resseq(num)
                 if res0 < 0:
                     sys.exit(f"[ERR] resid {num} non trovato nella topologia per {ra}{na}-{rb}{nb}")

@@ -2,9 +2,9 @@
 
 Frames are independent (every output row depends on one frame, CAVIAR-1.0.py:118-119), so rank r owns the
 contiguous frame range ``frame_shard(T, r, world)``, the pair / triplet lists are replicated, per-frame outputs
-stay rank-local (concatenated in rank order when gathered) and the path has exactly ONE exchange step: a sum
-all-reduce of the per-feature aggregates {occupancy, sum, sum of squares} -- NCCL over NVLink on the GPUs, gloo
-in the CPU tests.  Integer occupancies are bit-exact under any reduction order.
+stay rank-local (concatenated in rank order when gathered) and the path has exactly ONE exchange step: ONE sum
+all-reduce of the per-feature aggregates {occupancy, sum, sum of squares} packed into a float64 buffer -- NCCL over
+NVLink on the GPUs, gloo in the CPU tests.  Integer occupancies stay bit-exact (counts < 2^53 are exact in float64).
 """
 from __future__ import annotations
 
@@ -57,18 +57,48 @@ def frame_shard(n_frames: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def reduce_aggregates(occupancy, sums, group=None):
-    """In-place sum all-reduce of the aggregates over the process group.
+def pack_aggregates(occupancy, sum_=None, sumsq=None, out=None):
+    """The exchange buffer of the path: ONE float64 tensor [occupancy | sum | sumsq] (3F, or F without the moments).
 
-    ``occupancy``: int64 tensor (F,), ``sums``: float64 tensor (2, F) = [sum, sumsq].  Two collectives (the two
-    dtypes cannot share a buffer); 24*F bytes in total -- latency-bound on NVLink 5, so NCCL's stock all-reduce is
-    used rather than a fused kernel.
+    Occupancy counts are frame counts: integers below 2^53 are exact in float64 and so is their sum in any order, so
+    the integer bit-exactness of the reduced occupancy survives the single-dtype buffer (checked: ``unpack`` refuses a
+    value that is not an integer).  One collective instead of two halves the latency-bound exchange step.
+    """
+    import torch
+    F = occupancy.shape[0]
+    n = F if sum_ is None else 3 * F
+    if out is None:
+        out = torch.empty(n, dtype=torch.float64, device=occupancy.device)
+    out[:F].copy_(occupancy)                  # int64 -> float64, exact below 2^53
+    if sum_ is not None:
+        out[F:2 * F].copy_(sum_)
+        out[2 * F:].copy_(sumsq)
+    return out
+
+
+def unpack_aggregates(buf, occupancy, sum_=None, sumsq=None):
+    """Inverse of ``pack_aggregates`` into the caller's tensors (occupancy int64)."""
+    F = occupancy.shape[0]
+    occupancy.copy_(buf[:F])                  # float64 -> int64: exact for the integers a sum of counts can be
+    if sum_ is not None:
+        sum_.copy_(buf[F:2 * F])
+        sumsq.copy_(buf[2 * F:])
+    return occupancy, sum_, sumsq
+
+
+def reduce_aggregates(occupancy, sums=None, group=None, buf=None):
+    """In-place sum all-reduce of the aggregates over the process group: ONE collective over the packed float64
+    buffer (8*F or 24*F bytes) -- latency-bound on NVLink 5, so NCCL's stock all-reduce is used.
+
+    ``occupancy``: int64 tensor (F,); ``sums``: float64 tensor (2, F) = [sum, sumsq], or None for occupancy-only
+    (contact-map) runs.
     """
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return occupancy, sums
-    dist.all_reduce(occupancy, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    buf = pack_aggregates(occupancy, None if sums is None else sums[0], None if sums is None else sums[1], out=buf)
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    unpack_aggregates(buf, occupancy, None if sums is None else sums[0], None if sums is None else sums[1])
     return occupancy, sums
 
 
@@ -101,8 +131,10 @@ def sharded_features_host(plan, xyz_shard: np.ndarray, box_shard=None, group=Non
             backend = dist.get_backend(group)
             dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
             occ = torch.from_numpy(res["occupancy"].astype(np.int64)).to(dev)
-            sums = torch.from_numpy(np.stack([res["sum"], res["sumsq"]])).to(dev)
+            # lean (contact-map) runs return the occupancy alone: the moments are reduced only when they exist
+            sums = torch.from_numpy(np.stack([res["sum"], res["sumsq"]])).to(dev) if "sum" in res else None
             reduce_aggregates(occ, sums, group)
             res["occupancy"] = occ.cpu().numpy().astype(np.uint64)
-            res["sum"], res["sumsq"] = sums[0].cpu().numpy(), sums[1].cpu().numpy()
+            if sums is not None:
+                res["sum"], res["sumsq"] = sums[0].cpu().numpy(), sums[1].cpu().numpy()
     return res

@@ -114,6 +114,8 @@ def read_pdb(path: str) -> Topology:
     last = None
     with open(path, "r", errors="ignore") as fh:
         for line in fh:
+            if line.startswith("ENDMDL"):
+                break                                               # a multi-MODEL file: the first model is the topology
             if not (line.startswith("ATOM") or line.startswith("HETATM")):
                 continue
             key = (line[21], line[22:27])
@@ -258,6 +260,20 @@ class Trajectory:
                 raise ValueError(f"{path}: expected a (T, N, 3) array")
             self._len = self._ang = None
         else:
+            # everything else must be a NetCDF-3 file (Amber .nc / .ncdf): look at the magic bytes before handing the
+            # file to scipy, whose errors on foreign formats are opaque
+            with open(path, "rb") as fh:
+                magic = fh.read(8)
+            if magic[:3] != b"CDF" or magic[3:4] not in (b"\x01", b"\x02"):
+                if magic[:8] == b"\x89HDF\r\n\x1a\n":
+                    what = "NetCDF-4 / HDF5 (convert with `cpptraj` or `ncks -3` to NetCDF-3, the Amber convention)"
+                elif ext == ".xtc":
+                    what = "GROMACS XTC (compressed coordinates are not read; convert to .trr, .dcd or .nc)"
+                elif ext in (".mdcrd", ".crd", ".trj"):
+                    what = "Amber ASCII mdcrd (not read; convert to .nc)"
+                else:
+                    what = f"unknown format '{ext or path}'"
+                sys.exit(f"[ERR] formato di traiettoria non supportato: {what}. Supportati: Amber NetCDF-3 (.nc), DCD, TRR, .npy")
             from scipy.io import netcdf_file
             self._nc = netcdf_file(path, "r", mmap=True)
             if "coordinates" not in self._nc.variables:

@@ -306,3 +306,29 @@ def test_trr_trajectories_and_gro_topology(ext, tmp_path, box, vel):
     top = trajio.read_topology(str(gro))
     assert top.n_atoms == 6 and top.res_labels == ["ASP", "GLU"] and [top.atom_of(0), top.atom_of(1)] == [1, 4]
     assert ext.select_atoms(top, [("ASP", 1, "GLU", 2)], "resSeq", 0).tolist() == [[1, 4]]
+
+
+def test_unsupported_inputs_fail_with_a_clear_message(ext, tmp_path):
+    """The formats the reference's help text lists but this reader does not take (Extractor:99) exit with [ERR],
+    not with a scipy traceback; resSeq numbering needs a topology that carries residue numbers."""
+    from caviar_b200 import trajio
+    for name, head in (("t.xtc", b"\x00\x00\x07\xcb" + b"\0" * 60), ("t.mdcrd", b"title\n  1.000  2.000\n"),
+                       ("t4.nc", b"\x89HDF\r\n\x1a\n" + b"\0" * 60), ("t.foo", b"whatever")):
+        p = tmp_path / name
+        p.write_bytes(head)
+        with pytest.raises(SystemExit) as e:
+            trajio.Trajectory(str(p))
+        assert "[ERR] formato di traiettoria non supportato" in str(e.value), name
+    names, labels, first = ["N", "CA", "C"] * 4, ["ALA", "GLY", "SER", "THR"], [0, 3, 6, 9]
+    top_path = tmp_path / "s.prmtop"
+    trajio.write_prmtop(str(top_path), names, labels, first)
+    top = trajio.read_topology(str(top_path))
+    with pytest.raises(SystemExit) as e:
+        ext.select_atoms(top, [("ALA", 1, "GLY", 2)], "resSeq", 0)
+    assert "resSeq" in str(e.value) and "[ERR]" in str(e.value)
+    # a multi-MODEL PDB is one topology, not the models concatenated
+    pdb = tmp_path / "m.pdb"
+    model = "".join("ATOM  %5d  CA  %3s A%4d    %8.3f%8.3f%8.3f\n" % (k + 1, labels[k], 10 + k, k, 0.0, 0.0) for k in range(4))
+    pdb.write_text("MODEL        1\n" + model + "ENDMDL\nMODEL        2\n" + model + "ENDMDL\nEND\n")
+    t = trajio.read_topology(str(pdb))
+    assert t.n_atoms == 4 and t.n_res == 4 and t.res_seq == [10, 11, 12, 13]

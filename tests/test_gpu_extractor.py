@@ -101,3 +101,25 @@ def test_extractor_error_paths(tmp_path):
     with pytest.raises(SystemExit) as e:
         extractor.main(["--top", top, "--traj", nc, "--pairs", "ASP5-GLU30", "--offset", "21"])
     assert "label-offset < 1" in str(e.value)
+
+
+def test_drop_in_reproduces_the_reference_main_byte_for_byte(tmp_path, capsys, golden_dir, monkeypatch):
+    """B2 / a10: same command lines as tests/golden/extractor/cases.json (CSV, stdout produced by the UNMODIFIED
+    reference main() with oracle/cpptraj_stub.py as cpptraj): the drop-in's CSV must be identical byte for byte --
+    header, '#Frame' set index, 4 decimals, CR LF line ends -- and so must the two stdout lines."""
+    import os
+    import shutil
+    from caviar_b200 import extractor
+    gdir = os.path.join(golden_dir, "extractor")
+    with open(os.path.join(gdir, "cases.json")) as fh:
+        cases = json.load(fh)["cases"]
+    work = tmp_path / "w"
+    shutil.copytree(gdir, work)
+    monkeypatch.chdir(work)
+    for c in cases:
+        out = f"dropin_{c['csv']}"
+        argv = [out if a == c["csv"] else a for a in c["argv"]]
+        assert extractor.main(argv) == 0
+        printed = capsys.readouterr().out
+        assert open(work / out, "rb").read() == open(os.path.join(gdir, c["csv"]), "rb").read(), c["name"]
+        assert printed.replace(out, c["csv"]) == open(os.path.join(gdir, c["stdout"])).read(), c["name"]

@@ -48,8 +48,11 @@ def _worker(rank, world, port, T, q):
         sums = torch.from_numpy(np.stack([s1, s2]))
         reduce_aggregates(occ, sums)
         full = gather_frames(d, T)
+        # occupancy-only (contact-map) exchange, with counts far beyond 2^31 to show the float64 buffer keeps them exact
+        big = torch.tensor([(1 << 52) - 3 + rank, 5 * rank, 0], dtype=torch.int64)
+        reduce_aggregates(big, None)
         if rank == 0:
-            q.put((occ.numpy(), sums.numpy(), full))
+            q.put((occ.numpy(), sums.numpy(), full, big.numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -65,7 +68,7 @@ def test_two_rank_reduce_matches_single_process():
     procs = [ctx.Process(target=_worker, args=(r, world, port, T, q)) for r in range(world)]
     for p in procs:
         p.start()
-    occ, sums, full = q.get(timeout=120)
+    occ, sums, full, big = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -77,6 +80,21 @@ def test_two_rank_reduce_matches_single_process():
     s1, s2 = orc.moment_sums(d)
     np.testing.assert_allclose(sums[0], s1, rtol=1e-14)
     np.testing.assert_allclose(sums[1], s2, rtol=1e-14)
+    assert big.tolist() == [2 * ((1 << 52) - 3) + 1, 5, 0]
+
+
+def test_packed_exchange_buffer_round_trips():
+    import torch
+    from caviar_b200.sharding import pack_aggregates, unpack_aggregates
+    occ = torch.tensor([0, 7, (1 << 53) - 1], dtype=torch.int64)
+    s1, s2 = torch.tensor([0.5, -1.25, 3e300]), torch.tensor([1.0, 2.0, 3.0])
+    s1, s2 = s1.double(), s2.double()
+    buf = pack_aggregates(occ, s1, s2)
+    assert buf.dtype == torch.float64 and buf.shape == (9,)
+    o2, a2, b2 = torch.zeros(3, dtype=torch.int64), torch.zeros(3, dtype=torch.float64), torch.zeros(3, dtype=torch.float64)
+    unpack_aggregates(buf, o2, a2, b2)
+    assert torch.equal(o2, occ) and torch.equal(a2, s1) and torch.equal(b2, s2)
+    assert pack_aggregates(occ).shape == (3,)
 
 
 def test_numa_binding_helper_is_a_no_op_without_topology():
