@@ -6,14 +6,21 @@
            bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference --steps 3 --warmup 1      # the reference's CPU path on the host cores
 
-One "step" = one pass of the fused hot path (distances, angles, flags, scores, occupancy / moment
-aggregates) over the rank's whole shard of frames, resident in HBM in the staged layout, followed -- when
-N > 1 -- by the single NCCL all-reduce of the per-feature aggregates.  Frames are sharded across ranks
-(weak scaling: every rank owns --frames frames).  Prints ONE JSON line on rank 0.
+One "step" = one pass of the WHOLE device path over the rank's shard of frames: the fused kernel reads the frames as
+the trajectory holds them -- raw float32 xyz of the selected atoms, sliced in the plan's order (CAVIAR-1.0.py:335 with
+``plan.atom_order``) -- and writes distances, angles, flags, scores and the occupancy / moment aggregates; nothing is
+pre-wrapped, pre-converted or otherwise staged outside the timed region.  With N > 1 the step ends with the single
+NCCL all-reduce of the per-feature aggregates.  Frames are sharded across ranks (weak scaling: every rank owns
+--frames frames).  Prints ONE JSON line on rank 0.
+
+Also on that line: ``caller_order_input`` (frames compact in the CALLER's atom order: permutation kernel K0 + fused
+kernel), ``raw_frame_input`` (whole (T, N, 3) frames), ``all_configs`` (the other BASELINE.json shapes), and
+``config5_sharded`` (BASELINE config 5, its 500 000 frames split over the N ranks -- the multi-GPU case BASELINE names).
 """
 from __future__ import annotations
 
 import argparse
+import importlib.util
 import json
 import os
 import subprocess
@@ -30,6 +37,7 @@ if ROOT not in sys.path:
 METRIC = "pair-distance evals/sec (frames x (pairs + triplets) / s)"
 UNIT = "evals/s"
 CUTS = dict(pair_cutoff=8.0, hbond_dist_cutoff=3.0, hbond_angle_cutoff=135.0)
+BOX_BYTES = {None: 0, "ortho": 12, "triclinic": 36}
 
 
 def parse_args():
@@ -42,9 +50,11 @@ def parse_args():
     ap.add_argument("--frames", type=int, default=0, help="frames per rank (0 = the config's frame count)")
     ap.add_argument("--e2e-frames", type=int, default=4096, help="frames per end-to-end step (host buffers)")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-frames", type=int, default=1000, help="frames of the CPU baseline sample")
-    ap.add_argument("--direct-frames", type=int, default=4096, help="frames of the raw-frame (direct gather) side measurement; 0 = skip")
+    ap.add_argument("--cpu-frames", type=int, default=1000, help="frames of the CPU baseline sample (SURVEY 8d: 1000-2000)")
+    ap.add_argument("--side-frames", type=int, default=32768, help="frames of the caller-order side measurement; 0 = skip")
+    ap.add_argument("--direct-frames", type=int, default=4096, help="frames of the raw-frame side measurement; 0 = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-all-configs", action="store_true")
     return ap.parse_args()
 
 
@@ -122,20 +132,46 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(cfg_id, n_frames):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the fused kernel, per launch, from the committed ncu
-    --set full capture (profiles/traffic.json holds bytes per frame of that capture; scaled to this launch)."""
+def profile_record(key):
+    """One entry of profiles/traffic.json (ncu --set full captures, summarised by tools/make_profiles.py)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            rec = json.load(fh)
-        return rec[f"cfg{cfg_id}"]["dram_bytes_per_frame"] * n_frames
+            return json.load(fh).get(key)
     except Exception:
         return None
 
 
+def ncu_traffic(key, n_frames):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the kernel, per launch: bytes per frame of the committed capture
+    scaled to this launch's frame count."""
+    rec = profile_record(key)
+    return rec["dram_bytes_per_frame"] * n_frames if rec and "dram_bytes_per_frame" in rec else None
+
+
+def load_synthetic():
+    """caviar_b200/synthetic.py by file path: the workload generator without importing the package (the CPU arms must not
+    map the product's shared library)."""
+    spec = importlib.util.spec_from_file_location("_caviar_synthetic", os.path.join(ROOT, "caviar_b200", "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["_caviar_synthetic"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
 # ---------------------------------------------------------------------------------------------------------
-# CPU arms (oracle port of the reference; the only place bench.py touches oracle/)
+# CPU arms (the reference itself where it is on this machine, else its port; the only place bench.py touches oracle/)
 # ---------------------------------------------------------------------------------------------------------
+def reference_operator():
+    """(compute_distances_parallel, kind): the reference's own function through the SURVEY 8c stub loader when
+    /root/reference exists (build container), the oracle's restatement of it otherwise (GPU box)."""
+    from oracle import ref_loader
+    ref = ref_loader.load()
+    if ref is not None:
+        return ref.compute_distances_parallel, "reference"
+    from oracle import caviar_oracle as orc
+    return orc.pair_distances, "port"
+
+
 def cpu_reference_pass(x, box, pairs, triplets, n_jobs):
     """One pass of the reference's CPU path over the sample: compute_distances_parallel (CAVIAR-1.0.py:110-122,
     no PBC -- the reference has none), the per-pair time mean (:342) and the `< cut` threshold (:186), in numpy
@@ -144,8 +180,9 @@ def cpu_reference_pass(x, box, pairs, triplets, n_jobs):
     Returns seconds per part."""
     from oracle import c_oracle as co
     from oracle import caviar_oracle as orc
+    op, kind = reference_operator()
     t0 = time.perf_counter()
-    d = orc.pair_distances(x, [tuple(p) for p in pairs.tolist()], n_jobs=n_jobs)
+    d = op(x, [tuple(p) for p in pairs.tolist()], n_jobs=n_jobs)
     t1 = time.perf_counter()
     mean = orc.pair_time_mean(d)
     flags = orc.contact_flags(d, CUTS["pair_cutoff"])
@@ -155,10 +192,10 @@ def cpu_reference_pass(x, box, pairs, triplets, n_jobs):
     if len(triplets):
         ang, dac = co.triplet_angles(x, triplets, box, n_threads=n_jobs, with_end_distances=True)
         hb = orc.hbond_flags(dac, ang, CUTS["hbond_dist_cutoff"], CUTS["hbond_angle_cutoff"])
-        occ_t = orc.occupancy(hb)
+        orc.occupancy(hb)
     t3 = time.perf_counter()
     return {"pairs_s": t1 - t0, "aggregate_s": t2 - t1, "triplets_s": t3 - t2, "total_s": t3 - t0,
-            "dist": d, "angle": ang, "mean": mean, "occ": occ}
+            "dist": d, "angle": ang, "mean": mean, "occ": occ, "kind": kind}
 
 
 def cpu_fused_c_pass(x, box, pairs, triplets, n_jobs):
@@ -171,20 +208,28 @@ def cpu_fused_c_pass(x, box, pairs, triplets, n_jobs):
     return time.perf_counter() - t0, r
 
 
+def cpu_sample_text(cfg, T, r):
+    who = "the reference's own compute_distances_parallel (unmodified, stub-loaded)" if r["kind"] == "reference" else \
+        "the oracle's port of compute_distances_parallel (the reference is not on this machine)"
+    return (f"{T} frames of {cfg.name}, compact (T,U,3) input as the reference feeds it (CAVIAR-1.0.py:335): {who}, numpy + joblib "
+            f"threads, no PBC (it has none) {r['pairs_s']:.2f}s + mean/threshold {r['aggregate_s']:.2f}s + triplet angles with "
+            f"27-image PBC in the C oracle (cpptraj stand-in) {r['triplets_s']:.2f}s")
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's CPU implementation of the path, timed on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from caviar_b200 import synthetic as syn
+    syn = load_synthetic()
     top = syn.make_topology(args.config)
     cfg = top.cfg
     pairs, triplets = syn.compact_indices(top)
-    T = max(50, min(args.cpu_frames, 500))
+    T = max(50, min(args.cpu_frames, 2000))
     x = syn.parity_frames(top, T, only_referenced=True)
     box = syn.boxes_for(top, T)
     n_jobs = max((os.cpu_count() or 2) - 1, 1)
-    times = []
+    times, r = [], None
     for i in range(args.warmup + args.steps):
         r = cpu_reference_pass(x, box, pairs, triplets, n_jobs)
         if i >= args.warmup:
@@ -192,16 +237,15 @@ def run_reference_arm(args):
     ms = 1e3 * float(np.mean(times))
     evals = T * (len(pairs) + len(triplets))
     value = evals / (ms * 1e-3)
-    sample = (f"{T} frames of {cfg.name} (compact (T,U,3) input as the reference feeds it, CAVIAR-1.0.py:335); "
-              f"pairs via the reference algorithm without PBC (it has none: numpy + joblib threads), triplets with "
-              f"27-image PBC via the C oracle on the same threads (cpptraj stand-in)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(cfg, T, len(pairs), len(triplets), len(top.referenced)),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_jobs, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_jobs, "kind": r["kind"], "sample": cpu_sample_text(cfg, T, r)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0,
+            # this arm must not touch the product: its shared library is not even mapped into the process
+            "product_library_mapped": any("libcaviar_b200" in ln for ln in open("/proc/self/maps"))}
     print(json.dumps(line), flush=True)
 
 
@@ -216,6 +260,81 @@ def workload_config(cfg, frames_per_rank, P, A, U, **extra):
 # ---------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------
+class DeviceWorkload:
+    """One BASELINE config resident on the device in the layout its plan reads: plan-order raw float32 frames for
+    staged plans (sliced with plan.atom_order -- done once here, as whoever reads the trajectory does), the caller's
+    compact frames for zero-copy / direct plans.  ``step(n)`` runs the whole device path over n logical frames by
+    cycling over the resident block (the big configs do not fit; every launch streams the block from HBM)."""
+
+    def __init__(self, cb, syn, cfg_id, block_frames, dev, seed=0, want=("dist", "angle", "flags", "score"), moments=True):
+        import torch
+        self.torch = torch
+        self.top = syn.make_topology(cfg_id)
+        self.cfg = self.top.cfg
+        pairs, triplets = syn.compact_indices(self.top)
+        self.U, self.P, self.A = len(self.top.referenced), len(pairs), len(triplets)
+        self.plan = cb.FeaturePlan(self.U, pairs, triplets if self.A else None, box=self.cfg.box, **CUTS)
+        self.info = self.plan.info
+        self.block = block_frames
+        staged = self.info["mode_name"] == "staged"
+        self.S = int(self.info["staged_floats_per_frame"]) if staged else 3 * self.U
+        self.coords = torch.empty((block_frames, self.S // 3, 3), dtype=torch.float32, device=dev)
+        box_np = syn.boxes_for(self.top, block_frames)
+        self.box_np = box_np
+        self.rec = self.plan.prepare_box(torch.from_numpy(box_np).to(dev)) if box_np is not None else None
+        chunk = max(1, min(block_frames, (1 << 30) // (self.U * 12)))
+        self.chunk = chunk
+        self.seed = seed
+        for t0 in range(0, block_frames, chunk):
+            t1 = min(block_frames, t0 + chunk)
+            raw = syn.device_frames(self.top, t1 - t0, device=dev, seed=seed + t0, only_referenced=True)
+            if staged:
+                self.plan.stage(raw, out=self.coords[t0:t1].view(t1 - t0, self.S))     # = raw[:, plan.atom_order, :]
+            else:
+                self.coords[t0:t1].copy_(raw)
+            del raw
+        self.out = self.plan.alloc_outputs(block_frames, want=want, device=dev)
+        self.agg_f = torch.zeros((2, self.plan.F), dtype=torch.float64, device=dev) if moments else None
+        self.agg = cb.Aggregates(torch.zeros(self.plan.F, dtype=torch.int64, device=dev),
+                                 None if not moments else self.agg_f[0], None if not moments else self.agg_f[1])
+        self.ws = self.plan.new_workspace(dev)
+        self.launches = 0
+        # algorithmic bytes per frame of THIS output selection (SURVEY 8d: a disabled store leaves B_alg)
+        self.alg_bytes = (12 * self.U + BOX_BYTES[self.cfg.box] + (4 * self.P if self.out.dist is not None else 0)
+                          + (4 * self.A if self.out.angle is not None else 0)
+                          + (4 * self.plan.W if self.out.flags is not None else 0) + (4 if self.out.score is not None else 0))
+
+    def zero(self):
+        self.agg.occupancy.zero_()
+        if self.agg_f is not None:
+            self.agg_f.zero_()
+
+    def step(self, n_frames=None):
+        n_frames = self.block if n_frames is None else n_frames
+        self.launches = 0
+        for t0 in range(0, n_frames, self.block):
+            n = min(self.block, n_frames - t0)
+            self.plan.run(self.coords, self.rec, out=self.out, aggregates=self.agg, workspace=self.ws, n_frames=n)
+            self.launches += self.plan.last_launches
+
+    def close(self):
+        self.plan.close()
+        self.coords = self.out = self.rec = self.ws = None
+
+
+def event_time(torch, fn, reps, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -227,6 +346,7 @@ def main():
 
     import caviar_b200 as cb
     from caviar_b200 import synthetic as syn
+    from caviar_b200.sharding import pack_aggregates, unpack_aggregates
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -240,7 +360,6 @@ def main():
         # one process per GPU: keep this rank's threads and page-locked buffers on the GPU's own NUMA node
         from caviar_b200.sharding import bind_to_gpu_numa_node
         numa_node = bind_to_gpu_numa_node(local_rank)
-    if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL writes its version banner to stdout (C level) when the communicator comes up; rank 0's stdout must
         # carry exactly ONE JSON line, so file descriptor 1 points at stderr until the first collective is through.
@@ -257,46 +376,35 @@ def main():
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
 
-    top = syn.make_topology(args.config)
-    cfg = top.cfg
-    T = args.frames or cfg.n_frames
-    pairs, triplets = syn.compact_indices(top)       # compact numbering of the U referenced atoms
-    U, P, A = len(top.referenced), len(pairs), len(triplets)
-
-    t_setup = time.perf_counter()
-    plan = cb.FeaturePlan(U, pairs, triplets, box=cfg.box, **CUTS)
-    info = plan.info
-    S = int(info["staged_floats_per_frame"]) if info["mode_name"] == "staged" else 3 * U
-    # ---- resident inputs: the rank's whole shard in the layout the fused kernel streams ----
-    coords = torch.empty((T, S) if info["mode_name"] == "staged" else (T, U, 3), dtype=torch.float32, device=dev)
-    box_np = syn.boxes_for(top, T)
-    rec = plan.prepare_box(torch.from_numpy(box_np).to(dev)) if box_np is not None else None
-    chunk = max(1, min(T, (1 << 30) // (U * 12)))
-    for t0 in range(0, T, chunk):
-        t1 = min(T, t0 + chunk)
-        raw = syn.device_frames(top, t1 - t0, device=dev, seed=1000 * rank + t0, only_referenced=True)
-        if info["mode_name"] == "staged":
-            plan.stage(raw, None if rec is None else rec[t0:t1], out=coords[t0:t1])
-        else:
-            coords[t0:t1].copy_(raw)
-    del raw
-    out = plan.alloc_outputs(T, device=dev)
-    agg_f = torch.zeros((2, plan.F), dtype=torch.float64, device=dev)
-    agg = cb.Aggregates(torch.zeros(plan.F, dtype=torch.int64, device=dev), agg_f[0], agg_f[1])
-    ws = plan.new_workspace(dev)
-    torch.cuda.synchronize()
-    t_setup = time.perf_counter() - t_setup
-
-    def step():
-        agg.occupancy.zero_(); agg_f.zero_()
-        plan.run(coords, rec, out=out, aggregates=agg, workspace=ws)
-        if world > 1:                                   # the one exchange step of the path
-            dist.all_reduce(agg.occupancy); dist.all_reduce(agg_f)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    peak, peak_src = measured_peak()
+
+    # ---- resident inputs: the rank's whole shard, raw float32 frames in plan order ----
+    t_setup = time.perf_counter()
+    T = args.frames or syn.CONFIGS[args.config].n_frames
+    wl = DeviceWorkload(cb, syn, args.config, T, dev, seed=1000 * rank)
+    plan, info, cfg, top = wl.plan, wl.info, wl.cfg, wl.top
+    U, P, A, S = wl.U, wl.P, wl.A, wl.S
+    xbuf = torch.empty(3 * plan.F, dtype=torch.float64, device=dev)      # the packed exchange buffer
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t_setup
+
+    def exchange():
+        """The one exchange step of the path: ONE sum all-reduce of [occupancy | sum | sumsq] as float64 (counts are
+        integers < 2^53: exact in any order)."""
+        pack_aggregates(wl.agg.occupancy, wl.agg_f[0], wl.agg_f[1], out=xbuf)
+        dist.all_reduce(xbuf)
+        unpack_aggregates(xbuf, wl.agg.occupancy, wl.agg_f[0], wl.agg_f[1])
+
+    def step():
+        wl.zero()
+        wl.step()
+        if world > 1:
+            exchange()
 
     sampler = ClockSampler(local_rank)           # samples through warm-up and the timed region (both are load)
     sampler.start()
@@ -304,17 +412,17 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    launches_per_step = plan.last_launches
+    launches_per_step = wl.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
            torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     for k in range(args.steps):
         ev[k][0].record()
-        agg.occupancy.zero_(); agg_f.zero_()
-        plan.run(coords, rec, out=out, aggregates=agg, workspace=ws)
+        wl.zero()
+        wl.step()
         ev[k][1].record()
         if world > 1:
-            dist.all_reduce(agg.occupancy); dist.all_reduce(agg_f)
+            exchange()
         ev[k][2].record()
     barrier()
     clocks = sampler.stop()
@@ -329,71 +437,219 @@ def main():
     evals_per_step = world * T * (P + A)
     value = evals_per_step / (ms_per_step * 1e-3)
 
-    # ---- size-independent property at the full size: checksum of checksums (sum of frame scores == sum of
-    #      occupancies == number of set flag bits), on the outputs of the last timed step ----
-    score_sum = out.score.sum(dtype=torch.int64)
-    bits = out.flags.view(torch.uint8)
+    # ---- the exchange step, before / after packing (N > 1): two collectives (i64[F], f64[2F]) against one f64[3F] ----
+    exchange_ab = None
+    if world > 1:
+        def two_collectives():
+            dist.all_reduce(wl.agg.occupancy); dist.all_reduce(wl.agg_f)
+        barrier(); ms_two = event_time(torch, two_collectives, 50, warm=5)
+        barrier(); ms_one = event_time(torch, exchange, 50, warm=5)
+        t2 = torch.tensor([ms_two, ms_one], dtype=torch.float64, device=dev)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        exchange_ab = {"two_collectives_ms": float(t2[0]), "one_packed_f64_ms": float(t2[1]),
+                       "note": "back-to-back, no kernel in between (no rank skew): the collective alone"}
+        step()                                       # leave the aggregates of a whole step behind for the checks below
+
+    # ---- size-independent properties at the full size, on the outputs of the last step ----
+    out, agg = wl.out, wl.agg
     lut = torch.tensor([bin(i).count("1") for i in range(256)], dtype=torch.int64, device=dev)
+
+    def flag_counts_per_feature(flags):
+        """(P + A,) int64: set bits per feature over this rank's frames, from the stored flag words (independent of the
+        kernel's own occupancy accumulation)."""
+        words = flags.view(torch.int32)
+        cnt = torch.zeros(plan.W * 32, dtype=torch.int64, device=dev)
+        shifts = torch.arange(32, device=dev, dtype=torch.int32)
+        for c0 in range(0, words.shape[0], 4096):
+            w = words[c0:c0 + 4096]
+            bits = (w.unsqueeze(-1) >> shifts) & 1                           # (n, W, 32)
+            cnt += bits.sum(0, dtype=torch.int64).reshape(-1)
+        wp = (P + 31) // 32
+        return torch.cat([cnt[:P], cnt[32 * wp:32 * wp + A]])
+
+    score_sum = out.score.sum(dtype=torch.int64)
+    bits8 = out.flags.view(torch.uint8)
     bit_sum = torch.zeros((), dtype=torch.int64, device=dev)
-    for c0 in range(0, bits.shape[0], 8192):
-        bit_sum += lut[bits[c0:c0 + 8192].long()].sum()
+    for c0 in range(0, bits8.shape[0], 8192):
+        bit_sum += lut[bits8[c0:c0 + 8192].long()].sum()
+    per_feature = flag_counts_per_feature(out.flags)
     sums = torch.stack([score_sum, bit_sum])
     if world > 1:
         dist.all_reduce(sums)                       # scores / flags are rank-local, the occupancy is already global
+        dist.all_reduce(per_feature)
     occ_sum = int(agg.occupancy.sum())
     full_check = {"score_sum": int(sums[0]), "flag_bits": int(sums[1]), "occupancy_sum": occ_sum,
-                  "equal": bool(int(sums[0]) == int(sums[1]) == occ_sum)}
+                  "equal": bool(int(sums[0]) == int(sums[1]) == occ_sum),
+                  "occupancy_equals_flag_counts_per_feature": bool(torch.equal(per_feature, agg.occupancy)),
+                  "features_checked": int(plan.F)}
+    if world > 1:
+        # Shard boundaries: every rank's FIRST and LAST frame, recomputed by rank 0 alone from the same global frame ids
+        # (the generator is a function of (rank, chunk start): rank 0 regenerates the two chunks and runs them through
+        # its own plan), must equal what the owning rank holds -- distances, angles, flags and score, bit for bit.
+        last_t0 = (T - 1) // wl.chunk * wl.chunk
+        mine = torch.cat([out.dist[0], out.angle[0] if A else out.dist[0, :0], out.dist[T - 1], out.angle[T - 1] if A else out.dist[0, :0]])
+        mine_i = torch.cat([out.flags[0], out.score[0:1], out.flags[T - 1], out.score[T - 1:T]])
+        gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        gathered_i = [torch.empty_like(mine_i) for _ in range(world)] if rank == 0 else None
+        dist.gather(mine, gathered, dst=0)
+        dist.gather(mine_i, gathered_i, dst=0)
+        if rank == 0:
+            ok = True
+            probe_out = plan.alloc_outputs(1, device=dev)
+            for r in range(world):
+                got_f, got_i = [], []
+                for t0, t in ((0, 0), (last_t0, T - 1)):
+                    n = min(wl.chunk, T - t0)
+                    raw = syn.device_frames(top, n, device=dev, seed=1000 * r + t0, only_referenced=True)
+                    one = plan.stage(raw[t - t0:t - t0 + 1].contiguous()) if info["mode_name"] == "staged" else raw[t - t0:t - t0 + 1].contiguous()
+                    plan.run(one, None if wl.rec is None else wl.rec[t:t + 1], out=probe_out, workspace=wl.ws, n_frames=1)
+                    got_f += [probe_out.dist[0].clone()] + ([probe_out.angle[0].clone()] if A else [])
+                    got_i += [probe_out.flags[0].clone(), probe_out.score[0:1].clone()]
+                    del raw
+                ok = ok and torch.equal(torch.cat(got_f).view(torch.int32), gathered[r].view(torch.int32)) \
+                    and torch.equal(torch.cat(got_i), gathered_i[r])
+            full_check["shard_boundary_frames_match_single_rank_recomputation"] = bool(ok)
+            full_check["ranks_checked"] = world
 
     # ---- roofline of the fused kernel (algorithmic bytes per launch / its average duration) ----
-    peak, peak_src = measured_peak()
     alg_bytes = int(info["algorithmic_bytes_per_frame"]) * T
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(args.config, T), "kernel": "cv::features_kernel<BOX=2,PIPE,FRAC> (+finalize)",
+                "traffic": ncu_traffic(f"cfg{args.config}", T),
+                "kernel": "cv::features_kernel<BOX,PIPE,LEAN> from raw plan-order float32 frames (+ finalize_kernel); no staging kernel",
                 "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "frac_of_nominal_8000": achieved / 8000.0,      # north_star's target is quoted on the ~8 TB/s nominal peak
                 "streamed_bytes_per_launch": T * (S * 4 + 4 * info["boxrec_floats_per_frame"] * info["n_tiles"]
                                                   + 4 * P + 4 * A + 4 * plan.W + 4)}
+    coords_gb = 4.0 * T * S / 1e9
+    rec_main = wl.rec
+    box_np = wl.box_np
+    wl.close()
+    del out, agg
+    torch.cuda.empty_cache()
 
-    # ---- raw (T, N, 3) frames resident in HBM: compaction (K0) + fused kernel, and the direct-gather kernel ----
+    # ---- the same frames compact in the CALLER's atom order: permutation kernel K0 + fused kernel ----
+    caller = None
+    if args.side_frames > 0 and world == 1 and info["mode_name"] == "staged":
+        Tc = min(args.side_frames, T)
+        with cb.FeaturePlan(U, *syn.compact_indices(top), box=cfg.box, **CUTS) as cplan:
+            raw = syn.device_frames(top, Tc, device=dev, seed=31, only_referenced=True)
+            rec = None if rec_main is None else rec_main[:Tc]
+            staged = torch.empty((Tc, S), dtype=torch.float32, device=dev)
+            o = cplan.alloc_outputs(Tc, device=dev)
+            ag = cplan.new_aggregates(dev)
+            cws = cplan.new_workspace(dev)
+            ms_k0 = event_time(torch, lambda: cplan.stage(raw, out=staged), 5)
+            ms_both = event_time(torch, lambda: cplan.run(cplan.stage(raw, out=staged), rec, out=o, aggregates=ag, workspace=cws), 5)
+            alg = int(info["algorithmic_bytes_per_frame"]) * Tc
+            caller = {"input": f"({Tc}, {U}, 3) float32 compact frames in the caller's atom order, resident in HBM",
+                      "value": Tc * (P + A) / (ms_both * 1e-3), "unit": UNIT, "ms": ms_both, "k0_ms": ms_k0,
+                      "k0_copy_gbs": (12 * U + 4 * S) * Tc / ms_k0 / 1e6, "roofline_frac": alg / (ms_both * 1e-3) / 1e9 / peak,
+                      "traffic": None if ncu_traffic("cfg3_k0", Tc) is None or ncu_traffic("cfg3", Tc) is None
+                      else ncu_traffic("cfg3_k0", Tc) + ncu_traffic("cfg3", Tc),
+                      "note": "a 12-byte atom costs a 32-byte sector wherever it is gathered from: the permutation is L2-transaction "
+                              "bound, which is why the hand-over format of staged plans is the plan order (value above)"}
+            del raw, staged, o, ag, cws
+
+    # ---- raw (T, N, 3) frames resident in HBM: K0 from whole frames + fused kernel, and the direct-gather kernel ----
     direct = None
-    if args.direct_frames > 0 and world == 1:
-        del coords
+    if args.direct_frames > 0 and world == 1 and cfg.n_atoms * 12 * args.direct_frames < 40e9:
         Td = min(args.direct_frames, T)
         raw = syn.device_frames(top, Td, device=dev, seed=77, only_referenced=False)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 5
-
-        def timed(fn):
-            for _ in range(3):
-                fn()
-            torch.cuda.synchronize()
-            e0.record()
-            for _ in range(reps):
-                fn()
-            e1.record()
-            torch.cuda.synchronize()
-            return e0.elapsed_time(e1) / reps
-
-        with cb.FeaturePlan(cfg.n_atoms, top.pairs, top.triplets, box=cfg.box, **CUTS) as fplan:
+        rec = None if rec_main is None else rec_main[:Td]
+        with cb.FeaturePlan(cfg.n_atoms, top.pairs, top.triplets if A else None, box=cfg.box, **CUTS) as fplan:
             fws = fplan.new_workspace(dev)
-            staged_buf = torch.empty((Td, int(fplan.info["staged_floats_per_frame"])), dtype=torch.float32, device=dev)
-            ms_stage = timed(lambda: fplan.stage(raw, None if rec is None else rec[:Td], out=staged_buf))
-            ms_both = timed(lambda: fplan.run(fplan.stage(raw, None if rec is None else rec[:Td], out=staged_buf), rec[:Td], out=out, aggregates=agg,
-                                              workspace=fws, n_frames=Td))
-            del staged_buf
-        with cb.FeaturePlan(cfg.n_atoms, top.pairs, top.triplets, box=cfg.box, force="direct", **CUTS) as dplan:
+            o = fplan.alloc_outputs(Td, device=dev)
+            ag = fplan.new_aggregates(dev)
+            if fplan.info["mode_name"] == "staged":
+                staged_buf = torch.empty((Td, int(fplan.info["staged_floats_per_frame"])), dtype=torch.float32, device=dev)
+                ms_stage = event_time(torch, lambda: fplan.stage(raw, out=staged_buf), 5)
+                ms_both = event_time(torch, lambda: fplan.run(fplan.stage(raw, out=staged_buf), rec, out=o, aggregates=ag, workspace=fws), 5)
+                del staged_buf
+            else:
+                ms_stage = 0.0
+                ms_both = event_time(torch, lambda: fplan.run(raw, rec, out=o, aggregates=ag, workspace=fws), 5)
+        with cb.FeaturePlan(cfg.n_atoms, top.pairs, top.triplets if A else None, box=cfg.box, force="direct", **CUTS) as dplan:
             dws = dplan.new_workspace(dev)
-            ms_direct = timed(lambda: dplan.run(raw, rec[:Td], out=out, aggregates=agg, workspace=dws, n_frames=Td))
+            ms_direct = event_time(torch, lambda: dplan.run(raw, rec, out=o, aggregates=ag, workspace=dws), 5)
         alg = int(info["algorithmic_bytes_per_frame"]) * Td
         direct = {"input": f"raw ({Td}, {cfg.n_atoms}, 3) frames resident in HBM (12*N = {12 * cfg.n_atoms} B per frame)",
                   "compaction_plus_fused": {"value": Td * (P + A) / (ms_both * 1e-3), "unit": UNIT, "ms": ms_both,
                                             "compaction_ms": ms_stage, "roofline_frac": alg / (ms_both * 1e-3) / 1e9 / peak},
                   "direct_gather": {"value": Td * (P + A) / (ms_direct * 1e-3), "unit": UNIT, "ms": ms_direct,
                                     "roofline_frac": alg / (ms_direct * 1e-3) / 1e9 / peak}}
-        del raw
+        del raw, o, ag
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE config 5 as BASELINE states it: its 500 000 frames split over the N ranks + the NCCL reduce ----
+    def config_run(cfg_id, frames_total, block, reps, want=("dist", "angle", "flags", "score"), moments=True, shard=False):
+        """Whole-job time of one BASELINE shape: frames_total logical frames (split over the ranks when shard), cycled
+        over a resident block of `block` frames per rank; every launch streams the block from HBM (block >> L2)."""
+        lo, hi = (0, frames_total)
+        if shard:
+            from caviar_b200.sharding import frame_shard
+            lo, hi = frame_shard(frames_total, rank, world)
+        mine = hi - lo
+        w = DeviceWorkload(cb, syn, cfg_id, max(1, min(block, mine)), dev, seed=7000 + 1000 * rank, want=want, moments=moments)
+        xb = torch.empty((3 if moments else 1) * w.plan.F, dtype=torch.float64, device=dev)
+
+        def one():
+            w.zero()
+            w.step(mine)
+            if shard and world > 1:
+                pack_aggregates(w.agg.occupancy, None if not moments else w.agg_f[0], None if not moments else w.agg_f[1], out=xb)
+                dist.all_reduce(xb)
+                unpack_aggregates(xb, w.agg.occupancy, None if not moments else w.agg_f[0], None if not moments else w.agg_f[1])
+        if shard:
+            barrier()
+        ms = event_time(torch, one, reps, warm=1)
+        if shard and world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        evals = frames_total * (w.P + w.A)
+        alg = w.alg_bytes * mine                               # per GPU
+        res = {"workload": f"config {cfg_id}: {w.cfg.description}", "frames_total": frames_total, "frames_per_gpu": mine,
+               "resident_block_frames": w.block, "launches_per_step": w.launches, "plan_mode": w.info["mode_name"],
+               "outputs": list(want) + (["occupancy", "sum", "sumsq"] if moments else ["occupancy"]),
+               "ms": ms, "value": evals / (ms * 1e-3), "unit": UNIT,
+               "algorithmic_bytes_per_frame": w.alg_bytes, "roofline_frac_per_gpu": alg / (ms * 1e-3) / 1e9 / peak,
+               "input": "raw float32 frames in plan order" if w.info["mode_name"] == "staged" else "the caller's frames as they are (no K0 in this mode)"}
+        occ_total = int(w.agg.occupancy.sum())
+        res["occupancy_sum"] = occ_total
+        w.close()
+        torch.cuda.empty_cache()
+        return res
+
+    cfg5 = config_run(5, syn.CONFIGS[5].n_frames, 8192, 2, shard=True)
+    cfg5["parallelism"] = f"frames sharded over {world} rank(s), one packed NCCL all-reduce of the aggregates per pass"
+    cfg5["scaling"] = "strong (500 000 frames in total at every N)"
+    cfg5["traffic"] = ncu_traffic("cfg5", cfg5["frames_per_gpu"])
+
+    # ---- the other BASELINE shapes on one GPU (device-resident, everything inside) ----
+    all_configs = None
+    if world == 1 and not args.no_all_configs:
+        all_configs = {"cfg5": cfg5}
+        all_configs["cfg1"] = config_run(1, syn.CONFIGS[1].n_frames, 1000, 20)
+        all_configs["cfg1"]["note"] = "7 MB of traffic: launch-latency bound (two launches per step), reported, not tuned for"
+        all_configs["cfg2"] = config_run(2, syn.CONFIGS[2].n_frames, 10000, 10)
+        c4 = config_run(4, syn.CONFIGS[4].n_frames, 2048, 2)
+        c4["traffic"] = ncu_traffic("cfg4", c4["frames_per_gpu"])
+        c4["note"] = "all-pairs list, distances emitted: HBM-write bound in principle (1.98 MB of stores per frame)"
+        all_configs["cfg4_distances_emitted"] = c4
+        c4l = config_run(4, syn.CONFIGS[4].n_frames, 2048, 2, want=("flags", "score"), moments=False)
+        # issue roofline: warp instructions per frame (ncu, profiles/traffic.json) x frames/s / (SMs x 4 schedulers x clock)
+        rec4 = profile_record("cfg4_lean")
+        if rec4 and "warp_instructions_per_frame" in rec4 and clocks.get("sm_mhz"):
+            ips = rec4["warp_instructions_per_frame"] * c4l["frames_total"] / (c4l["ms"] * 1e-3)
+            c4l["issue_roofline_frac"] = ips / (148 * 4 * clocks["sm_mhz"] * 1e6)
+            c4l["warp_instructions_per_32_evals"] = rec4["warp_instructions_per_frame"] * 32.0 / syn.CONFIGS[4].n_pairs
+        c4l["note"] = "contact map as BASELINE names config 4 (fused cutoff scoring and occupancy output): issue-bound, not HBM-bound"
+        all_configs["cfg4_contact_map"] = c4l
 
     # ---- end to end through the reference-facing host call (pinned host buffers, H2D + D2H inside) ----
+    plan = cb.FeaturePlan(U, *syn.compact_indices(top), box=cfg.box, **CUTS)
+    pairs, triplets = plan.pairs, plan.triplets
     Te = min(args.e2e_frames, T)
     xh = torch.empty((Te, U, 3), dtype=torch.float32).pin_memory()
     xh.copy_(syn.device_frames(top, Te, device=dev, seed=4242 + rank, only_referenced=True).cpu())
@@ -410,7 +666,8 @@ def main():
         if world > 1:
             o = torch.from_numpy(res["occupancy"].astype(np.int64)).to(dev)
             s = torch.from_numpy(np.stack([res["sum"], res["sumsq"]])).to(dev)
-            dist.all_reduce(o); dist.all_reduce(s)
+            b = pack_aggregates(o, s[0], s[1])
+            dist.all_reduce(b)
             torch.cuda.synchronize()
         return res
 
@@ -426,12 +683,44 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te[0])
-    box_b = {None: 0, "ortho": 12, "triclinic": 36}[cfg.box]
     e2e = {"value": world * Te * (P + A) / e2e_s, "unit": UNIT,
-           "h2d_bytes_per_step": Te * (U * 12 + box_b),
+           "h2d_bytes_per_step": Te * (U * 12 + BOX_BYTES[cfg.box]),
            "d2h_bytes_per_step": Te * (4 * P + 4 * A + 4 * plan.W + 4) + 24 * plan.F,
            "frames_per_step": Te, "ms_per_step": 1e3 * e2e_s,
-           "call": "FeaturePlan.features_host -> caviar_features_host (pinned host buffers)"}
+           "call": "FeaturePlan.features_host -> caviar_features_host (pinned host buffers, caller-order compact frames; "
+                   "H2D, K0, fused kernel, D2H double-buffered)"}
+
+    # ---- what the host links can carry with all N ranks copying at once (the ceiling of e2e at N > 1) ----
+    if world > 1:
+        nbytes = 256 << 20
+        hb_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        hb_out = torch.empty(nbytes // 6, dtype=torch.uint8).pin_memory()      # e2e moves ~6x more in than out
+        db_in = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        db_out = torch.empty(nbytes // 6, dtype=torch.uint8, device=dev)
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def copies():
+            with torch.cuda.stream(s_in):
+                db_in.copy_(hb_in, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                hb_out.copy_(db_out, non_blocking=True)
+        for _ in range(2):
+            copies()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(8):
+            copies()
+        s_in.synchronize(); s_out.synchronize()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        agg_gbs = world * 8 * (nbytes + nbytes // 6) / float(dt[0]) / 1e9
+        moved = e2e["h2d_bytes_per_step"] + e2e["d2h_bytes_per_step"]
+        e2e["host_link_ceiling"] = {"what": f"{world} ranks x (256 MiB H2D + 43 MiB D2H) cudaMemcpyAsync loops at the same time, pinned buffers",
+                                    "aggregate_gbs": agg_gbs, "per_gpu_gbs": agg_gbs / world,
+                                    "e2e_moves_gbs": world * moved / e2e_s / 1e9,
+                                    "e2e_fraction_of_ceiling": (world * moved / e2e_s / 1e9) / agg_gbs}
+        del hb_in, hb_out, db_in, db_out
 
     # ---- CPU baseline beside it (rank 0, N = 1): bounded sample of the same workload ----
     cpu = None
@@ -453,10 +742,8 @@ def main():
         c_s, rc = cpu_fused_c_pass(xs, box_e[:Tc] if box_e is not None else None, pairs, triplets, n_jobs)
         if P and cfg.box is not None:
             check["max_dist_err_A_vs_c_oracle"] = float(np.abs(res["dist"].astype(np.float64) - rc["dist"]).max())
-        cpu = {"value": Tc * (P + A) / r["total_s"], "unit": UNIT, "cores": n_jobs, "kind": "port",
-               "sample": f"{Tc} frames of {cfg.name}: reference compute_distances_parallel algorithm (numpy, no PBC, joblib "
-                         f"threads) {r['pairs_s']:.2f}s + mean/threshold {r['aggregate_s']:.2f}s + triplet angles with "
-                         f"27-image PBC in the C oracle (cpptraj stand-in) {r['triplets_s']:.2f}s",
+        cpu = {"value": Tc * (P + A) / r["total_s"], "unit": UNIT, "cores": n_jobs, "kind": r["kind"],
+               "sample": cpu_sample_text(cfg, Tc, r),
                "pairs_only_value": Tc * P / max(r["pairs_s"] + r["aggregate_s"], 1e-9),
                "c_fused_value": Tc * (P + A) / max(c_s, 1e-9),
                "c_fused_note": f"whole path incl. PBC as one multi-threaded C pass (oracle/caviar_oracle.c), {rc['threads']} threads, {c_s:.2f}s",
@@ -465,7 +752,7 @@ def main():
     # ---- the reference's own shape through its own operator (B1), pageable numpy in / numpy out ----
     native = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import caviar_oracle as orc          # cpu_baseline leg: the checker / CPU arm, never the product
+        op, kind = reference_operator()                   # cpu_baseline leg: the checker / CPU arm, never the product
         Tn, nres = 7000, 300                              # T=7000, 300 residues, minsep 5
         rng = np.random.default_rng(0)
         Xn = (np.cumsum(rng.normal(0, 0.38, size=(nres, 3)), axis=0)[None]
@@ -476,33 +763,35 @@ def main():
         for _ in range(3):
             t0 = time.perf_counter(); Dn = cb.compute_distances_parallel(Xn, pl); ts.append(time.perf_counter() - t0)
         n_jobs = max((os.cpu_count() or 2) - 1, 1)
-        t0 = time.perf_counter(); Dr = orc.pair_distances(Xn, pl, n_jobs=n_jobs); cpu_s = time.perf_counter() - t0
+        t0 = time.perf_counter(); Dr = op(Xn, pl, n_jobs=n_jobs); cpu_s = time.perf_counter() - t0
         native = {"call": "compute_distances_parallel(X (7000,300,3), all pairs minsep 5 -> P=43660)  [CAVIAR-1.0.py:110-122]",
                   "ours_s": min(ts), "ours_evals_per_s": Tn * len(pl) / min(ts), "cpu_s": cpu_s, "cpu_threads": n_jobs,
-                  "cpu_evals_per_s": Tn * len(pl) / cpu_s, "bit_exact": bool(Dn.tobytes() == Dr.tobytes())}
+                  "cpu_kind": kind, "cpu_evals_per_s": Tn * len(pl) / cpu_s, "bit_exact": bool(Dn.tobytes() == Dr.tobytes())}
         del Dn, Dr
+    plan.close()
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(cfg, T, P, A, U, plan=info, l2="inputs (%.1f GB per rank) >> 126 MB L2, no flush needed"
-                                          % (coords_bytes(T, S) / 1e9), setup_s=round(t_setup, 1),
-                                          parallelism=f"frame-sharded x{world}, one NCCL all-reduce of aggregates per step",
+                "config": workload_config(cfg, T, P, A, U, plan=info,
+                                          input="raw float32 xyz of the referenced atoms, sliced in plan order (atom_slice(plan.atom_order), "
+                                                "CAVIAR-1.0.py:335): %d slots = %d distinct atoms + per-tile repeats / padding; "
+                                                "no wrap, no conversion, no staging kernel before the timed region" % (S // 3, U),
+                                          l2="inputs (%.1f GB per rank) >> 126 MB L2, no flush needed" % coords_gb,
+                                          setup_s=round(t_setup, 1),
+                                          parallelism=f"frame-sharded x{world}, one packed NCCL all-reduce of the aggregates per step",
                                           rank0_numa_node=numa_node),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
                 "gpu_launches": launches_per_step * args.steps,
-                "exchange": {"what": "NCCL sum all-reduce of occupancy i64[F] + {sum, sumsq} f64[2F] (24*F bytes)",
-                             "bytes": 24 * plan.F, "ms_per_step": reduce_ms if world > 1 else 0.0},
-                "raw_frame_input": direct,
+                "exchange": {"what": "ONE NCCL sum all-reduce of [occupancy | sum | sumsq] packed as f64[3F] (24*F bytes; "
+                                     "occupancy counts < 2^53 stay exact)",
+                             "bytes": 24 * (P + A), "ms_per_step": reduce_ms if world > 1 else 0.0, "before_after": exchange_ab},
+                "caller_order_input": caller, "raw_frame_input": direct, "config5_sharded": cfg5, "all_configs": all_configs,
                 "reference_native_shape": native, "full_size_check": full_check}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
-
-
-def coords_bytes(T, S):
-    return 4.0 * T * S
 
 
 if __name__ == "__main__":

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_bench_line_contract():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "1", "--steps", "3", "--warmup", "3",
                           "--frames", "4096", "--e2e-frames", "512", "--e2e-steps", "1", "--direct-frames", "256",
-                          "--cpu-frames", "50"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                          "--side-frames", "2048", "--cpu-frames", "50"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
                          timeout=900, cwd=ROOT)
     assert res.returncode == 0, res.stderr[-3000:]
     lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
@@ -32,8 +32,15 @@ def test_bench_line_contract():
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
     c = d["cpu_baseline"]
-    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["spot_check"]["max_angle_err_deg"] <= 1e-3
+    assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["value"] > 0 and c["spot_check"]["max_angle_err_deg"] <= 1e-3
     assert d["value"] > 100 * c["value"]
     assert d["reference_native_shape"]["bit_exact"] is True
     assert d["full_size_check"]["equal"] is True and d["full_size_check"]["score_sum"] > 0
+    assert d["full_size_check"]["occupancy_equals_flag_counts_per_feature"] is True
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    # staging is inside the number: the timed input is raw frames in plan order, and the caller-order / other-config legs exist
+    assert "no staging kernel" in d["config"]["input"] and d["caller_order_input"]["k0_ms"] > 0
+    assert set(d["all_configs"]) == {"cfg1", "cfg2", "cfg4_distances_emitted", "cfg4_contact_map", "cfg5"}
+    for name, c in d["all_configs"].items():
+        assert c["value"] > 0 and 0 < c["roofline_frac_per_gpu"] < 1.2, name
+    assert d["config5_sharded"]["frames_total"] == 500000 and d["config5_sharded"]["occupancy_sum"] > 0

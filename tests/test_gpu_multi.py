@@ -32,10 +32,13 @@ def _worker(rank, world, port, T, q):
         lo, hi = frame_shard(T, rank, world)
         with cb.FeaturePlan(x.shape[1], pairs, triplets, box="triclinic", device=rank) as plan:
             res = sharded_features_host(plan, x[lo:hi], box[lo:hi])
+            # contact-map (lean) run: occupancy only -- the exchange must not expect the moments
+            lean = sharded_features_host(plan, x[lo:hi], box[lo:hi], want=("flags", "score", "occ"))
+            assert "sum" not in lean
         dist_all = gather_frames(res["dist"], T)
         score_all = gather_frames(res["score"], T)
         if rank == 0:
-            q.put((res["occupancy"], res["sum"], res["sumsq"], dist_all, score_all))
+            q.put((res["occupancy"], res["sum"], res["sumsq"], dist_all, score_all, lean["occupancy"]))
     finally:
         dist.destroy_process_group()
 
@@ -54,7 +57,7 @@ def test_two_rank_sharding_matches_single_gpu():
     procs = [ctx.Process(target=_worker, args=(r, world, port, T, q)) for r in range(world)]
     for p in procs:
         p.start()
-    occ, s1, s2, dist_all, score_all = q.get(timeout=300)
+    occ, s1, s2, dist_all, score_all, occ_lean = q.get(timeout=300)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -66,5 +69,6 @@ def test_two_rank_sharding_matches_single_gpu():
     assert dist_all.tobytes() == one["dist"].tobytes()
     assert np.array_equal(score_all, one["score"])
     assert np.array_equal(occ, one["occupancy"])                 # integer aggregates: bit-exact across shardings
+    assert np.array_equal(occ_lean, one["occupancy"])
     np.testing.assert_allclose(s1, one["sum"], rtol=1e-13)
     np.testing.assert_allclose(s2, one["sumsq"], rtol=1e-13)
