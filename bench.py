@@ -294,9 +294,9 @@ class DeviceWorkload:
                 self.coords[t0:t1].copy_(raw)
             del raw
         self.out = self.plan.alloc_outputs(block_frames, want=want, device=dev)
-        self.agg_f = torch.zeros((2, self.plan.F), dtype=torch.float64, device=dev) if moments else None
-        self.agg = cb.Aggregates(torch.zeros(self.plan.F, dtype=torch.int64, device=dev),
-                                 None if not moments else self.agg_f[0], None if not moments else self.agg_f[1])
+        # ONE float64 buffer [occupancy | sum | sumsq]: the kernel accumulates the counts as float64 (exact < 2^53), so
+        # the multi-GPU exchange is a single all-reduce of this buffer, nothing to pack
+        self.agg_buf, self.agg = self.plan.new_packed_aggregates(dev, moments=moments)
         self.ws = self.plan.new_workspace(dev)
         self.launches = 0
         # algorithmic bytes per frame of THIS output selection (a disabled store leaves B_alg)
@@ -305,9 +305,7 @@ class DeviceWorkload:
                           + (4 * self.plan.W if self.out.flags is not None else 0) + (4 if self.out.score is not None else 0))
 
     def zero(self):
-        self.agg.occupancy.zero_()
-        if self.agg_f is not None:
-            self.agg_f.zero_()
+        self.agg_buf.zero_()
 
     def step(self, n_frames=None):
         n_frames = self.block if n_frames is None else n_frames
@@ -346,7 +344,7 @@ def main():
 
     import caviar_b200 as cb
     from caviar_b200 import synthetic as syn
-    from caviar_b200.sharding import pack_aggregates, unpack_aggregates
+    from caviar_b200.sharding import pack_aggregates
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -389,16 +387,13 @@ def main():
     wl = DeviceWorkload(cb, syn, args.config, T, dev, seed=1000 * rank)
     plan, info, cfg, top = wl.plan, wl.info, wl.cfg, wl.top
     U, P, A, S = wl.U, wl.P, wl.A, wl.S
-    xbuf = torch.empty(3 * plan.F, dtype=torch.float64, device=dev)      # the packed exchange buffer
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t_setup
 
     def exchange():
-        """The one exchange step of the path: ONE sum all-reduce of [occupancy | sum | sumsq] as float64 (counts are
-        integers < 2^53: exact in any order)."""
-        pack_aggregates(wl.agg.occupancy, wl.agg_f[0], wl.agg_f[1], out=xbuf)
-        dist.all_reduce(xbuf)
-        unpack_aggregates(xbuf, wl.agg.occupancy, wl.agg_f[0], wl.agg_f[1])
+        """The one exchange step of the path: ONE sum all-reduce of the float64 buffer [occupancy | sum | sumsq] the
+        kernels accumulated into (counts are integers < 2^53: exact in any order)."""
+        dist.all_reduce(wl.agg_buf)
 
     def step():
         wl.zero()
@@ -440,14 +435,17 @@ def main():
     # ---- the exchange step, before / after packing (N > 1): two collectives (i64[F], f64[2F]) against one f64[3F] ----
     exchange_ab = None
     if world > 1:
-        def two_collectives():
-            dist.all_reduce(wl.agg.occupancy); dist.all_reduce(wl.agg_f)
+        occ_i64 = torch.zeros(plan.F, dtype=torch.int64, device=dev)
+        sums_f64 = torch.zeros((2, plan.F), dtype=torch.float64, device=dev)
+
+        def two_collectives():                       # round 1: int64 occupancy and float64 moments cannot share a buffer
+            dist.all_reduce(occ_i64); dist.all_reduce(sums_f64)
         barrier(); ms_two = event_time(torch, two_collectives, 50, warm=5)
         barrier(); ms_one = event_time(torch, exchange, 50, warm=5)
         t2 = torch.tensor([ms_two, ms_one], dtype=torch.float64, device=dev)
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        exchange_ab = {"two_collectives_ms": float(t2[0]), "one_packed_f64_ms": float(t2[1]),
-                       "note": "back-to-back, no kernel in between (no rank skew): the collective alone"}
+        exchange_ab = {"two_collectives_ms": float(t2[0]), "one_f64_buffer_ms": float(t2[1]),
+                       "note": "back-to-back, no kernel in between (no rank skew): the collective(s) alone"}
         step()                                       # leave the aggregates of a whole step behind for the checks below
 
     # ---- size-independent properties at the full size, on the outputs of the last step ----
@@ -480,7 +478,8 @@ def main():
     occ_sum = int(agg.occupancy.sum())
     full_check = {"score_sum": int(sums[0]), "flag_bits": int(sums[1]), "occupancy_sum": occ_sum,
                   "equal": bool(int(sums[0]) == int(sums[1]) == occ_sum),
-                  "occupancy_equals_flag_counts_per_feature": bool(torch.equal(per_feature, agg.occupancy)),
+                  "occupancy_equals_flag_counts_per_feature": bool(torch.equal(per_feature, agg.occupancy.to(torch.int64))),
+                  "occupancy_is_integral": bool(torch.equal(agg.occupancy, agg.occupancy.round())),
                   "features_checked": int(plan.F)}
     if world > 1:
         # Shard boundaries: every rank's FIRST and LAST frame, recomputed by rank 0 alone from the same global frame ids
@@ -591,15 +590,12 @@ def main():
             lo, hi = frame_shard(frames_total, rank, world)
         mine = hi - lo
         w = DeviceWorkload(cb, syn, cfg_id, max(1, min(block, mine)), dev, seed=7000 + 1000 * rank, want=want, moments=moments)
-        xb = torch.empty((3 if moments else 1) * w.plan.F, dtype=torch.float64, device=dev)
 
         def one():
             w.zero()
             w.step(mine)
             if shard and world > 1:
-                pack_aggregates(w.agg.occupancy, None if not moments else w.agg_f[0], None if not moments else w.agg_f[1], out=xb)
-                dist.all_reduce(xb)
-                unpack_aggregates(xb, w.agg.occupancy, None if not moments else w.agg_f[0], None if not moments else w.agg_f[1])
+                dist.all_reduce(w.agg_buf)
         if shard:
             barrier()
         ms = event_time(torch, one, reps, warm=1)
@@ -784,8 +780,8 @@ def main():
                                           rank0_numa_node=numa_node),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
                 "gpu_launches": launches_per_step * args.steps,
-                "exchange": {"what": "ONE NCCL sum all-reduce of [occupancy | sum | sumsq] packed as f64[3F] (24*F bytes; "
-                                     "occupancy counts < 2^53 stay exact)",
+                "exchange": {"what": "ONE NCCL sum all-reduce of the f64[3F] buffer [occupancy | sum | sumsq] the kernels accumulate into "
+                                     "(24*F bytes; occupancy counts < 2^53 stay exact; no packing)",
                              "bytes": 24 * (P + A), "ms_per_step": reduce_ms if world > 1 else 0.0, "before_after": exchange_ab},
                 "caller_order_input": caller, "raw_frame_input": direct, "config5_sharded": cfg5, "all_configs": all_configs,
                 "reference_native_shape": native, "full_size_check": full_check}

@@ -57,7 +57,7 @@ class CvFrameOutputs(C.Structure):
 
 
 class CvAggregates(C.Structure):
-    _fields_ = [("occupancy", C.c_void_p), ("sum", C.c_void_p), ("sumsq", C.c_void_p)]
+    _fields_ = [("occupancy", C.c_void_p), ("sum", C.c_void_p), ("sumsq", C.c_void_p), ("occupancy_f64", C.c_void_p)]
 
 
 class CvHostOutputs(C.Structure):
@@ -79,6 +79,8 @@ SYMBOLS = {
     "caviar_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                              C.POINTER(CvFrameOutputs), C.POINTER(CvAggregates), C.c_void_p, C.c_void_p]),
     "caviar_last_launch_count": (C.c_int64, []),
+    "caviar_residue_components": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_double,
+                                            C.c_void_p, C.c_void_p]),
     "caviar_weighted_scores": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "caviar_features_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                        C.POINTER(CvHostOutputs), C.c_int64, C.c_int32]),

@@ -3,9 +3,10 @@
 The reference thresholds the per-pair TIME-MEAN distance and labels the connected components of the resulting
 residue graph (``build_residue_components``, CAVIAR-1.0.py:183-199, called at :497-499 and :785-786 with
 ``nm_cut = cluster_cut_A / 10``).  Here the mean comes straight from the kernel's fp64 ``sum`` aggregate
-(``sum[p] / T``, no second pass over the (T, P) matrix) and the components are found with a union-find instead of
-the reference's DFS; labels are assigned in order of the lowest residue index, which is exactly the order in which
-the reference's outer loop discovers components, so the label vectors are identical.
+(``sum[p] / T``, no second pass over the (T, P) matrix) and the components are found on the device
+(``FeaturePlan.residue_components`` -> ``caviar_residue_components``: label propagation in shared memory) or, for host
+arrays, with scipy's connected components; labels are assigned in order of the lowest residue index, which is exactly
+the order in which the reference's outer loop discovers components, so the label vectors are identical.
 """
 from __future__ import annotations
 
@@ -20,30 +21,23 @@ def pair_means_from_aggregates(sum_per_pair, n_frames: int, dtype=np.float32) ->
 
 
 def residue_components(n_res: int, pairs: Sequence[Tuple[int, int]], pair_means, cut: float) -> List[int]:
-    """Component label of every residue; an edge (i, j) exists iff ``float(mean_ij) < cut`` (strict, in double)."""
+    """Component label of every residue; an edge (i, j) exists iff ``float(mean_ij) < cut`` (strict, in double).
+    Host-side convenience over arrays (vectorised: scipy's connected components + a renumbering in the order of each
+    component's lowest residue); ``FeaturePlan.residue_components`` is the same on the device."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
     pairs = np.asarray(pairs, dtype=np.int64).reshape(-1, 2)
     means = np.asarray(pair_means, dtype=np.float64)
     if len(pairs) != len(means):
         raise ValueError("one mean per pair expected")
-    parent = np.arange(n_res, dtype=np.int64)
-
-    def find(a: int) -> int:
-        root = a
-        while parent[root] != root:
-            root = parent[root]
-        while parent[a] != root:
-            parent[a], a = root, parent[a]
-        return root
-
-    for (i, j) in pairs[means < float(cut)]:
-        ri, rj = find(int(i)), find(int(j))
-        if ri != rj:
-            parent[max(ri, rj)] = min(ri, rj)
-    labels, seen = [0] * n_res, {}
-    for r in range(n_res):
-        root = find(r)
-        labels[r] = seen.setdefault(root, len(seen))
-    return labels
+    edges = pairs[means < float(cut)]
+    graph = coo_matrix((np.ones(len(edges), dtype=np.int8), (edges[:, 0], edges[:, 1])), shape=(n_res, n_res))
+    _, raw = connected_components(graph, directed=False)
+    # renumber: component ids in the order of their first (= lowest) member, as the reference's outer loop finds them
+    _, first = np.unique(raw, return_index=True)
+    rank = np.empty(len(first), dtype=np.int64)
+    rank[np.argsort(first)] = np.arange(len(first))
+    return rank[raw].tolist()
 
 
 def cohens_d_from_aggregates(sum_a, sumsq_a, n_a: int, sum_b, sumsq_b, n_b: int) -> np.ndarray:

@@ -138,6 +138,7 @@ struct CvPlan {
     TileDesc* d_tiles = nullptr;
     int32_t *d_idx0 = nullptr, *d_idx1 = nullptr, *d_idx2 = nullptr;
     int32_t* d_src_off = nullptr;
+    int32_t* d_pairs = nullptr;        // [P][2] in the caller's numbering, uploaded on first use (caviar_residue_components)
     int* d_err = nullptr;
     mutable HostCtx host;     // cached resources of the host entry point
 };
@@ -190,7 +191,7 @@ extern "C" void caviar_plan_destroy(CvPlan* plan) {
     if (!plan) return;
     cudaFree(plan->d_tiles);
     cudaFree(plan->d_idx0); cudaFree(plan->d_idx1); cudaFree(plan->d_idx2);
-    cudaFree(plan->d_src_off); cudaFree(plan->d_err);
+    cudaFree(plan->d_src_off); cudaFree(plan->d_err); cudaFree(plan->d_pairs);
     delete plan;
 }
 
@@ -339,9 +340,10 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
     }
     if (!coords_dev) return fail(CV_E_INVALID, "null coordinate pointer");
     if (hp.desc.box_kind != CV_BOX_NONE && !boxrec_dev) return fail(CV_E_INVALID, "plan has a box but boxrec is null");
-    const bool want_agg = agg && (agg->occupancy || agg->sum || agg->sumsq);
+    const bool want_agg = agg && (agg->occupancy || agg->occupancy_f64 || agg->sum || agg->sumsq);
     const bool want_moments = want_agg && (agg->sum || agg->sumsq);
-    if (want_agg && !agg->occupancy) return fail(CV_E_INVALID, "aggregates: occupancy alone, or occupancy + sum + sumsq");
+    if (want_agg && !agg->occupancy && !agg->occupancy_f64) return fail(CV_E_INVALID, "aggregates: occupancy alone, or occupancy + sum + sumsq");
+    if (want_agg && agg->occupancy && agg->occupancy_f64) return fail(CV_E_INVALID, "aggregates: occupancy as uint64 OR as float64, not both");
     if (want_moments && !(agg->sum && agg->sumsq)) return fail(CV_E_INVALID, "aggregates: occupancy alone, or occupancy + sum + sumsq");
     if (!workspace_dev) return fail(CV_E_INVALID, "null workspace (CvPlanInfo.workspace_bytes of device memory)");
     cudaStream_t st = (cudaStream_t)stream;
@@ -436,13 +438,51 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
         const bool many = rp.n_chunks >= kFinalizeManyRows;      // (a function of the run's shape only: reproducible)
 #define CV_FINALIZE(M, S)                                                                                          \
         finalize_kernel<M, S><<<blocks, dim3(32, S), 0, st>>>(rp.occ_part, rp.sum_part, rp.sq_part, F, rp.n_chunks, \
-                                                              occ_out, agg->sum, agg->sumsq)
+                                                              occ_out, agg->occupancy_f64, agg->sum, agg->sumsq)
         if (want_moments) { if (many) CV_FINALIZE(true, kFinalizeSlicesMany); else CV_FINALIZE(true, kFinalizeSlicesFew); }
         else              { if (many) CV_FINALIZE(false, kFinalizeSlicesMany); else CV_FINALIZE(false, kFinalizeSlicesFew); }
 #undef CV_FINALIZE
         CV_CUDA(cudaGetLastError());
         g_launches += 1;
     }
+    return CV_OK;
+}
+
+// Thresholded mean-distance graph -> residue components, on the device (CAVIAR-1.0.py:183-199 with the means of :496 / :783).
+extern "C" int caviar_residue_components(const CvPlan* plan, const double* sum_dev, int64_t n_frames,
+                                         const double* sum_b_dev, int64_t n_frames_b, double cutoff,
+                                         int32_t* labels_dev, void* stream) {
+    g_launches = 0;
+    if (!plan) return fail(CV_E_INVALID, "null plan");
+    const HostPlan& hp = plan->hp;
+    if (hp.P <= 0) return fail(CV_E_INVALID, "the plan has no pairs");
+    if (!sum_dev || !labels_dev) return fail(CV_E_INVALID, "null argument");
+    if (n_frames <= 0 || (sum_b_dev && n_frames_b <= 0)) return fail(CV_E_INVALID, "frame counts must be positive");
+    const int n = hp.desc.n_atoms, threads = 1024;
+    const size_t smem = (size_t)(n + threads) * sizeof(int);
+    if (smem > 200 * 1024) return fail(CV_E_UNSUPPORTED, "more than ~50 000 residues: the label table does not fit in shared memory");
+    cudaStream_t st = (cudaStream_t)stream;
+    CvPlan* mp = const_cast<CvPlan*>(plan);
+    if (!mp->d_pairs) {
+        std::lock_guard<std::mutex> lock(mp->host.mu);
+        if (!mp->d_pairs) {
+            int32_t* d = nullptr;
+            CV_CUDA(cudaMalloc((void**)&d, hp.pairs.size() * sizeof(int32_t)));
+            cudaError_t e = cudaMemcpy(d, hp.pairs.data(), hp.pairs.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { cudaFree(d); return fail(CV_E_CUDA, std::string("pair upload: ") + cudaGetErrorString(e)); }
+            mp->d_pairs = d;
+        }
+    }
+    static int granted[64] = {0};
+    const int dev = plan->device & 63;
+    if ((int)smem > granted[dev] && smem > 48 * 1024) {
+        CV_CUDA(cudaFuncSetAttribute(components_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        granted[dev] = (int)smem;
+    }
+    components_kernel<<<1, threads, smem, st>>>(sum_dev, (double)n_frames, sum_b_dev, (double)std::max<int64_t>(n_frames_b, 1),
+                                                plan->d_pairs, hp.P, n, cutoff, labels_dev);
+    CV_CUDA(cudaGetLastError());
+    g_launches = 1;
     return CV_OK;
 }
 

@@ -1,0 +1,322 @@
+// Lagged covariance blocks of CAVIAR-1.0.py:396-402 (_cov_blocks: X0.T @ X0 / n, Xt.T @ Xt / n, X0.T @ Xt / n over
+// centred per-frame distances) on the 5th-generation tensor cores: hand-written tcgen05 / TMEM / TMA for sm_100a.
+//
+// This is the one dense contraction next to the hot path.  The reference multiplies float32
+// matrices with numpy's sgemm; a single TF32 pass (10-bit mantissa) would lose three decimal digits against that, so
+// every operand is split once into two TF32-exact halves, x = hi + lo with hi = rna_tf32(x) and lo = x - hi (exact),
+// and each product block is accumulated as  hi.hi + hi.lo + lo.hi  in the float32 accumulator held in TMEM ("3xTF32":
+// the dropped lo.lo term and the truncation of lo are ~2^-21 relative, the class of sgemm's own rounding).
+//
+//   cov_split_kernel   X (n, K) float32 [- mu] -> HI, LO (n, Kp) float32 planes (centring fused; HBM-bound, once per X)
+//   cov_gemm_kernel    C[i, j] = scale * sum_t A[t, i] * B[t, j]  for one 128 x 128 tile of C per CTA:
+//                        warp 0   TMA producer: 3-D tensor maps stream [32 frames x 128 features] boxes of the four
+//                                 planes (A.hi, A.lo, B.hi, B.lo) into a 3-stage shared-memory ring, 128-byte swizzled
+//                                 -- the operands are MN-major (features contiguous), which tcgen05 takes as they are:
+//                                 no transposed copy of the (n, K) matrix is ever made;
+//                        warp 1   MMA issuer: one elected thread issues tcgen05.mma.cta_group::1.kind::tf32
+//                                 (M = 128, N = 128, K = 8) x 4 k-steps x 3 terms per stage, accumulating in TMEM;
+//                                 tcgen05.commit releases the stage to the producer and, at the end, the accumulator;
+//                        warps 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns at a time, scale by 1/n, 128-byte row stores.
+//
+// Rows beyond n and columns beyond K are zero-filled by TMA (out-of-bounds boxes), so ragged shapes need no masks in
+// the main loop; the epilogue masks its stores.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <mutex>
+#include <string>
+
+#include "../../include/caviar_b200.h"
+
+namespace cvcov {
+
+constexpr int kTileM = 128, kTileN = 128;      // C tile per CTA (= UMMA M x N)
+constexpr int kBlockK = 32;                     // frames per pipeline stage (4 UMMA k-steps of 8)
+constexpr int kUmmaK = 8;                       // tf32: 32 bytes of K per instruction
+constexpr int kPanel = 32;                      // features per 128-byte swizzle row
+constexpr int kPanelBytes = kBlockK * 128;      // one [32 frames x 32 features] panel: 4 KB = 4 swizzle atoms of 1 KB
+constexpr int kPlaneBytes = (kTileM / kPanel) * kPanelBytes;     // one operand plane of a stage: 16 KB
+constexpr int kStageBytes = 4 * kPlaneBytes;    // A.hi, A.lo, B.hi, B.lo
+constexpr int kStages = 3;
+constexpr int kTmemCols = 128;                  // 128 lanes x 128 float32 columns
+constexpr int kThreads = 192;                   // 6 warps
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem], issued by ONE thread on behalf of the CTA
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// "all MMAs issued so far are done" -> one arrival on an mbarrier (implies tcgen05.fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Shared-memory matrix descriptor of an MN-major, 128-byte-swizzled operand plane (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start address >> 4, [16,30) leading byte offset >> 4 = distance between 32-feature panels,
+//   [32,46) stride byte offset >> 4 = distance between 8-frame swizzle atoms, [46,48) version = 1, [61,64) layout 2 = SW128
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)(kPanelBytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6), A = B = TF32 [7,10) [10,13), A and B MN-major
+// (bits 15, 16), N >> 3 at [17,23), M >> 4 at [24,29)
+constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+
+__global__ void __launch_bounds__(256)
+cov_split_kernel(const float* __restrict__ x, long long ld_x, const float* __restrict__ mu, long long n, int K, int Kp,
+                 float* __restrict__ hi, float* __restrict__ lo) {
+    const int c4 = blockIdx.x * blockDim.x + threadIdx.x;            // group of 4 columns
+    if (4 * c4 >= Kp) return;
+    float m[4] = {0.f, 0.f, 0.f, 0.f};
+    if (mu != nullptr)
+        for (int k = 0; k < 4; ++k) if (4 * c4 + k < K) m[k] = __ldg(mu + 4 * c4 + k);
+    for (long long t = blockIdx.y; t < n; t += gridDim.y) {
+        float4 h, l;
+        float* hp = &h.x;
+        float* lp = &l.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = 4 * c4 + k;
+            const float v = (c < K) ? __fsub_rn(__ldg(x + t * ld_x + c), m[k]) : 0.f;     // dist - mu (CAVIAR-1.0.py:381-382)
+            uint32_t hb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+            const float hv = __uint_as_float(hb & 0xFFFFE000u);
+            hp[k] = hv;
+            lp[k] = __fsub_rn(v, hv);                                                     // exact: |lo| <= 2^-11 |v|
+        }
+        reinterpret_cast<float4*>(hi + t * (long long)Kp)[c4] = h;
+        reinterpret_cast<float4*>(lo + t * (long long)Kp)[c4] = l;
+    }
+}
+
+struct GemmParams {
+    long long n;            // frames (reduction length)
+    int K;                  // valid columns of C in both directions
+    long long ld_c;         // floats between rows of C
+    float scale;            // 1 / max(1, n)
+    float* c;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+cov_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                const GemmParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    // 128-byte swizzle atoms must sit on 1 KB boundaries
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* bar_empty = bar_full + kStages;
+    uint64_t* bar_accum = bar_empty + kStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_accum + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * kTileM, n0 = blockIdx.x * kTileN;
+    const int n_kblocks = (int)((p.n + kBlockK - 1) / kBlockK);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
+        mbar_init(bar_accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {            // one warp allocates the accumulator columns and later frees them
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int kb = 0; kb < n_kblocks; ++kb) {
+                const int s = kb % kStages;
+                if (kb >= kStages) mbar_wait(bar_empty + s, ((kb / kStages) - 1) & 1);
+                unsigned char* st = smem + s * kStageBytes;
+                mbar_expect_tx(bar_full + s, kStageBytes);
+                // box = {32 features, 32 frames, 4 panels}: coordinates (0, first frame, first panel)
+                tma_load_3d(st + 0 * kPlaneBytes, &map_a_hi, bar_full + s, 0, kb * kBlockK, m0 / kPanel);
+                tma_load_3d(st + 1 * kPlaneBytes, &map_a_lo, bar_full + s, 0, kb * kBlockK, m0 / kPanel);
+                tma_load_3d(st + 2 * kPlaneBytes, &map_b_hi, bar_full + s, 0, kb * kBlockK, n0 / kPanel);
+                tma_load_3d(st + 3 * kPlaneBytes, &map_b_lo, bar_full + s, 0, kb * kBlockK, n0 / kPanel);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one elected thread) =====================
+        if (lane == 0) {
+            for (int kb = 0; kb < n_kblocks; ++kb) {
+                const int s = kb % kStages;
+                mbar_wait(bar_full + s, (kb / kStages) & 1);
+                tcgen05_fence_after();
+                const uint32_t base = smem_u32(smem + s * kStageBytes);
+#pragma unroll
+                for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
+                    // one k-step = one 8-frame swizzle atom: 1 KB further into every panel
+                    const uint64_t a_hi = smem_desc(base + 0 * kPlaneBytes + kk * 1024), a_lo = smem_desc(base + 1 * kPlaneBytes + kk * 1024);
+                    const uint64_t b_hi = smem_desc(base + 2 * kPlaneBytes + kk * 1024), b_lo = smem_desc(base + 3 * kPlaneBytes + kk * 1024);
+                    umma_tf32(tmem_base, a_lo, b_hi, kInstrDesc, (kb | kk) != 0);      // small terms first
+                    umma_tf32(tmem_base, a_hi, b_lo, kInstrDesc, 1);
+                    umma_tf32(tmem_base, a_hi, b_hi, kInstrDesc, 1);
+                }
+                umma_commit(bar_empty + s);                  // the stage may be refilled once these MMAs have read it
+            }
+            umma_commit(bar_accum);                          // accumulator complete
+        }
+    } else {
+        // ===================== epilogue: TMEM -> registers -> global =====================
+        // a warp may only touch the TMEM lanes of its own quarter: lanes [32 * (warp % 4), + 32)
+        const int q = warp & 3;
+        mbar_wait(bar_accum, 0);
+        tcgen05_fence_after();
+        const int row = m0 + 32 * q + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kTileN; c0 += 32) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < p.K) {
+                float* dst = p.c + (long long)row * p.ld_c + n0 + c0;
+                if (n0 + c0 + 32 <= p.K && (p.ld_c & 3) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]) * p.scale, __uint_as_float(v[j + 1]) * p.scale,
+                                                                          __uint_as_float(v[j + 2]) * p.scale, __uint_as_float(v[j + 3]) * p.scale);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (n0 + c0 + j < p.K) dst[j] = __uint_as_float(v[j]) * p.scale;
+                }
+            }
+        }
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ---- host side ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            sym = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(sym);
+    }();
+    return fn;
+}
+
+// (n, Kp) row-major float32 plane seen as {32 features, n frames, Kp / 32 panels}: a box {32, 32, 4} lands in shared
+// memory panel by panel, each panel 32 rows of 128 bytes, 128-byte swizzled -- the canonical MN-major UMMA operand.
+static bool make_map(CUtensorMap* map, const float* plane, long long n, int Kp) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)kPanel, (cuuint64_t)n, (cuuint64_t)(Kp / kPanel)};
+    const cuuint64_t strides[2] = {(cuuint64_t)Kp * 4, (cuuint64_t)kPanel * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)kPanel, (cuuint32_t)kBlockK, (cuuint32_t)(kTileM / kPanel)};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(plane), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace cvcov
+
+extern "C" int caviar_set_error(int code, const char* msg);     // cv_api.cu: thread-local last error
+
+extern "C" int64_t caviar_cov_padded_columns(int64_t n_cols) {
+    return (n_cols + cvcov::kTileM - 1) / cvcov::kTileM * cvcov::kTileM;
+}
+
+extern "C" int caviar_cov_split(const float* x_dev, int64_t ld_x, const float* mu_dev, int64_t n_rows, int64_t n_cols,
+                                float* hi_dev, float* lo_dev, void* stream) {
+    if (n_rows < 0 || n_cols <= 0 || ld_x < n_cols) return caviar_set_error(CV_E_INVALID, "cov_split: bad shape");
+    if (n_rows == 0) return CV_OK;
+    if (!x_dev || !hi_dev || !lo_dev) return caviar_set_error(CV_E_INVALID, "cov_split: null argument");
+    if ((reinterpret_cast<uintptr_t>(hi_dev) | reinterpret_cast<uintptr_t>(lo_dev)) & 127)
+        return caviar_set_error(CV_E_INVALID, "cov_split: planes must be 128-byte aligned");
+    if (n_cols > (1 << 30)) return caviar_set_error(CV_E_INVALID, "cov_split: too many columns");
+    const int Kp = (int)caviar_cov_padded_columns(n_cols);
+    dim3 grid((Kp / 4 + 255) / 256, (unsigned)std::min<int64_t>(n_rows, 16384));
+    cvcov::cov_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_dev, ld_x, mu_dev, n_rows, (int)n_cols, Kp, hi_dev, lo_dev);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return caviar_set_error(CV_E_CUDA, cudaGetErrorString(e));
+    return CV_OK;
+}
+
+extern "C" int caviar_cov_gemm(const float* a_hi_dev, const float* a_lo_dev, const float* b_hi_dev, const float* b_lo_dev,
+                               int64_t n_rows, int64_t n_cols, float* c_dev, int64_t ld_c, void* stream) {
+    using namespace cvcov;
+    if (n_rows <= 0 || n_cols <= 0 || ld_c < n_cols) return caviar_set_error(CV_E_INVALID, "cov_gemm: bad shape");
+    if (!a_hi_dev || !a_lo_dev || !b_hi_dev || !b_lo_dev || !c_dev) return caviar_set_error(CV_E_INVALID, "cov_gemm: null argument");
+    if ((reinterpret_cast<uintptr_t>(a_hi_dev) | reinterpret_cast<uintptr_t>(a_lo_dev) | reinterpret_cast<uintptr_t>(b_hi_dev) |
+         reinterpret_cast<uintptr_t>(b_lo_dev)) & 15)
+        return caviar_set_error(CV_E_INVALID, "cov_gemm: planes must be 16-byte aligned");
+    if (n_rows >= (1ll << 31)) return caviar_set_error(CV_E_INVALID, "cov_gemm: too many rows");
+    const int Kp = (int)caviar_cov_padded_columns(n_cols);
+    CUtensorMap maps[4];
+    const float* planes[4] = {a_hi_dev, a_lo_dev, b_hi_dev, b_lo_dev};
+    for (int i = 0; i < 4; ++i)
+        if (!make_map(&maps[i], planes[i], n_rows, Kp))
+            return caviar_set_error(CV_E_CUDA, "cov_gemm: cuTensorMapEncodeTiled failed (driver entry point missing or bad plane)");
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(cov_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes); });
+    if (attr_err != cudaSuccess) return caviar_set_error(CV_E_CUDA, cudaGetErrorString(attr_err));
+    GemmParams p;
+    p.n = n_rows; p.K = (int)n_cols; p.ld_c = ld_c; p.scale = 1.0f / (float)std::max<int64_t>(1, n_rows); p.c = c_dev;
+    dim3 grid(Kp / kTileN, Kp / kTileM);
+    cov_gemm_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return caviar_set_error(CV_E_CUDA, cudaGetErrorString(e));
+    return CV_OK;
+}

@@ -245,6 +245,16 @@ class FeaturePlan:
                           torch.zeros(self.F, dtype=torch.float64, device=device),
                           torch.zeros(self.F, dtype=torch.float64, device=device))
 
+    def new_packed_aggregates(self, device="cuda", moments: bool = True):
+        """Aggregates in ONE contiguous float64 buffer ``[occupancy | sum | sumsq]`` (3F, or F without the moments):
+        returns ``(buffer, Aggregates)`` whose fields are views of it.  Frame counts are exact in float64 below 2^53, so
+        the multi-GPU exchange step of the path is a single ``all_reduce(buffer)`` -- no second collective for an
+        integer tensor, nothing to pack or unpack -- and the reduced occupancy is still an exact integer."""
+        import torch
+        buf = torch.zeros((3 if moments else 1) * self.F, dtype=torch.float64, device=device)
+        F = self.F
+        return buf, Aggregates(buf[:F], buf[F:2 * F] if moments else None, buf[2 * F:] if moments else None)
+
     def new_workspace(self, device="cuda"):
         import torch
         return torch.empty(max(int(self.info["workspace_bytes"]), 8), dtype=torch.uint8, device=device)
@@ -296,15 +306,36 @@ class FeaturePlan:
             workspace = self._ws
         ws_ptr = workspace.data_ptr()
         if aggregates is not None:      # occupancy alone (sum = sumsq = None), or all three
-            ag = CvAggregates(aggregates.occupancy.data_ptr(),
+            occ = aggregates.occupancy
+            if occ.dtype not in (torch.int64, torch.float64) or not occ.is_contiguous() or occ.shape != (self.F,):
+                raise ValueError(f"occupancy must be a contiguous ({self.F},) int64 or float64 CUDA tensor")
+            f64 = occ.dtype == torch.float64        # counts as float64 (exact < 2^53): see new_packed_aggregates
+            ag = CvAggregates(None if f64 else occ.data_ptr(),
                               None if aggregates.sum is None else aggregates.sum.data_ptr(),
-                              None if aggregates.sumsq is None else aggregates.sumsq.data_ptr())
+                              None if aggregates.sumsq is None else aggregates.sumsq.data_ptr(),
+                              occ.data_ptr() if f64 else None)
             ag_ptr = C.byref(ag)
         check(_lib.lib.caviar_run(self._handle, coords.data_ptr(), stride,
                                   None if boxrec is None else boxrec.data_ptr(), T,
                                   C.byref(fo), ag_ptr, ws_ptr, self._stream_ptr()))
         self.last_launches = int(_lib.lib.caviar_last_launch_count())
         return out
+
+    def residue_components(self, sum_a, n_frames: int, cut: float, sum_b=None, n_frames_b: int = 0):
+        """Component label of every residue (= atom of this plan) on the device: ``build_residue_components``
+        (CAVIAR-1.0.py:183-199) over the per-pair time means ``sum / T`` -- or, with ``sum_b``, the pooled mean of two
+        ensembles (:496) -- thresholded strictly below ``cut`` in double (:186).  ``sum_a`` / ``sum_b``: the fp64 ``sum``
+        aggregates of ``run`` (CUDA tensors).  Returns an int32 CUDA tensor of n_atoms labels, numbered like the
+        reference's (in the order of each component's lowest residue)."""
+        import torch
+        for t in (sum_a, sum_b):
+            if t is not None and (not t.is_cuda or t.dtype != torch.float64 or not t.is_contiguous() or t.shape[0] < self.P):
+                raise ValueError("sums must be contiguous float64 CUDA tensors with at least P entries")
+        labels = torch.empty(self.n_atoms, dtype=torch.int32, device=sum_a.device)
+        check(_lib.lib.caviar_residue_components(self._handle, sum_a.data_ptr(), int(n_frames),
+                                                 None if sum_b is None else sum_b.data_ptr(), int(n_frames_b), float(cut),
+                                                 labels.data_ptr(), self._stream_ptr()))
+        return labels
 
     def weighted_scores(self, flags, weights):
         """Per-frame weighted interaction score from the packed flags of ``run``: ``sum_f w[f] * flag[t, f]``.

@@ -27,6 +27,7 @@
  *                                for callers whose frames are already compact in their own order.
  *   caviar_compact_frames_host   the same selection at the trajectory-file boundary
  *                                (cpptraj's masks, Extractor:133-138), on the host.
+ *   caviar_residue_components    CAVIAR-1.0.py:183-199 (mean-distance threshold :186 -> residue graph -> components).
  *   caviar_weighted_scores       north_star extension: per-frame scores weighted by the
  *                                abs_loading CAVIAR-1.0.py:141-147 publishes per pair.
  *   caviar_format_csv            CAVIAR_Distances-Extractor.py:196-198 (CSV rows).
@@ -135,6 +136,9 @@ typedef struct CvAggregates {
     uint64_t* occupancy;  /* [P + A] frames in which the flag was set */
     double*   sum;        /* [P + A] sum over frames of d (pairs) / angle (triplets) */
     double*   sumsq;      /* [P + A] sum of squares */
+    double*   occupancy_f64; /* alternative to `occupancy` (set exactly one of the two): the same counts accumulated as
+                                float64 -- exact below 2^53 -- so that occupancy, sum and sumsq can live in ONE
+                                contiguous float64 buffer and the multi-GPU exchange is a single sum all-reduce of it */
 } CvAggregates;
 
 /* Host-side planning only (no CUDA call): what plan_create would decide. */
@@ -193,6 +197,18 @@ int64_t caviar_last_launch_count(void);
  * flags_dev: [n_frames][n_flag_words] as written by caviar_run; all pointers are device pointers. */
 int caviar_weighted_scores(const CvPlan* plan, const uint32_t* flags_dev, int64_t n_frames,
                            const int64_t* weights_q32_dev, int64_t* score_q32_dev, void* stream);
+
+/* Residue clusters from the aggregates, on the device (CAVIAR-1.0.py:183-199 build_residue_components, fed at :496-499
+ * and :783-786 with the per-pair time-mean distances and nm_cut = cluster_cut / 10): residues = the plan's atoms, an
+ * edge (i, j) for every pair whose float32 time mean is below the cut-off, compared in double and strictly (:186):
+ *     mean_p = fl32(sum[p] / n_frames)                                            single run (:783)
+ *     mean_p = 0.5f * (fl32(sum[p] / n_frames) + fl32(sum_b[p] / n_frames_b))     pooled run (:496), sum_b_dev != NULL
+ * labels_dev [n_atoms] int32 receives the component id of every residue, ids numbered in the order of each
+ * component's lowest residue index -- the order in which the reference's DFS discovers them, so the label vector is
+ * the reference's.  sum_dev / sum_b_dev: the fp64 `sum` aggregates of caviar_run (first P entries are used). */
+int caviar_residue_components(const CvPlan* plan, const double* sum_dev, int64_t n_frames,
+                              const double* sum_b_dev, int64_t n_frames_b, double cutoff,
+                              int32_t* labels_dev, void* stream);
 
 /* Reference-facing, HOST buffers in and out (pageable or pinned).  Streams the
  * frames through pinned staging, double buffered.  Any output may be NULL.
