@@ -81,6 +81,10 @@ SYMBOLS = {
     "caviar_last_launch_count": (C.c_int64, []),
     "caviar_residue_components": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_double,
                                             C.c_void_p, C.c_void_p]),
+    "caviar_cov_padded_columns": (C.c_int64, [C.c_int64]),
+    "caviar_cov_split": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "caviar_cov_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_float,
+                                  C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "caviar_weighted_scores": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "caviar_features_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                        C.POINTER(CvHostOutputs), C.c_int64, C.c_int32]),

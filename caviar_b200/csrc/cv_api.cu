@@ -49,6 +49,8 @@ struct Trace {
 }  // namespace
 
 extern "C" const char* caviar_last_error(void) { return g_err.c_str(); }
+// other translation units of the library (cv_cov.cu) report through the same thread-local slot
+extern "C" int caviar_set_error(int code, const char* msg) { return fail(code, msg ? msg : ""); }
 extern "C" int caviar_abi_version(void) { return CV_ABI_VERSION; }
 extern "C" int64_t caviar_last_launch_count(void) { return g_launches; }
 

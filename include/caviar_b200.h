@@ -28,6 +28,7 @@
  *   caviar_compact_frames_host   the same selection at the trajectory-file boundary
  *                                (cpptraj's masks, Extractor:133-138), on the host.
  *   caviar_residue_components    CAVIAR-1.0.py:183-199 (mean-distance threshold :186 -> residue graph -> components).
+ *   caviar_cov_split / _gemm     CAVIAR-1.0.py:396-402 (_cov_blocks: X0.T @ X0 / n ... of the VAMP-2 scan) on tcgen05.
  *   caviar_weighted_scores       north_star extension: per-frame scores weighted by the
  *                                abs_loading CAVIAR-1.0.py:141-147 publishes per pair.
  *   caviar_format_csv            CAVIAR_Distances-Extractor.py:196-198 (CSV rows).
@@ -209,6 +210,30 @@ int caviar_weighted_scores(const CvPlan* plan, const uint32_t* flags_dev, int64_
 int caviar_residue_components(const CvPlan* plan, const double* sum_dev, int64_t n_frames,
                               const double* sum_b_dev, int64_t n_frames_b, double cutoff,
                               int32_t* labels_dev, void* stream);
+
+/* ---- lagged covariance blocks on the tensor cores (CAVIAR-1.0.py:396-402 _cov_blocks) ----
+ * C = A^T B / n for (n, K) float32 matrices of centred per-frame features, as three TF32 tensor-core products per
+ * block (hi.hi + hi.lo + lo.hi, float32 accumulation in TMEM): float32-class accuracy, not TF32's.
+ *
+ *   caviar_cov_padded_columns(K)   Kp = K rounded up to the 128-column tile: row pitch of the hi / lo planes.
+ *   caviar_cov_split               x (n rows, ld_x floats apart, K columns), optional mu[K] (the per-column mean to
+ *                                  subtract: dist - mu_pool, CAVIAR-1.0.py:381-382) -> hi, lo planes (n, Kp) float32,
+ *                                  128-byte aligned, hi + lo == x - mu exactly, both exactly representable in TF32 up
+ *                                  to the truncation of lo.  One pass, HBM-bound.
+ *   caviar_cov_gemm                c[i][j] (+)= scale * sum_t a[t][i] * b[t][j], i, j in [0, K): one 128 x 128 tile per
+ *                                  CTA, TMA -> shared memory -> tcgen05.mma.kind::tf32 -> TMEM -> global.
+ *                                  Row t of a / b is at plane + t * row_stride_floats (>= Kp, multiple of 4), so
+ *                                  a_* / b_* may be views of the SAME planes: X0 = X[:-tau], Xt = X[tau:] (pass
+ *                                  plane + tau * Kp), the even / odd rows of the reference's cross-validation
+ *                                  (stride 2 * Kp, :409-421).  accumulate != 0 adds to c (stacked ensembles).
+ *                                  scale is usually 1 / max(1, n_total) (:398-401).
+ * All pointers are device pointers; asynchronous on `stream`. */
+int64_t caviar_cov_padded_columns(int64_t n_cols);
+int caviar_cov_split(const float* x_dev, int64_t ld_x, const float* mu_dev, int64_t n_rows, int64_t n_cols,
+                     float* hi_dev, float* lo_dev, void* stream);
+int caviar_cov_gemm(const float* a_hi_dev, const float* a_lo_dev, const float* b_hi_dev, const float* b_lo_dev,
+                    int64_t n_rows, int64_t row_stride_floats, int64_t n_cols, float scale, int32_t accumulate,
+                    float* c_dev, int64_t ld_c, void* stream);
 
 /* Reference-facing, HOST buffers in and out (pageable or pinned).  Streams the
  * frames through pinned staging, double buffered.  Any output may be NULL.
