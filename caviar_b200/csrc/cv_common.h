@@ -8,6 +8,12 @@ constexpr int kConsumerThreads = 224;   // 7 warps evaluate features (+1 produce
 constexpr int kProducerThreads = 32;    // 1 warp drives the TMA pipeline (staged / zero-copy modes)
 constexpr int kFeatPerThread   = 4;     // features whose atom indices a thread keeps in registers
 constexpr int kTileWidth       = kConsumerThreads * kFeatPerThread;   // 896 features per column tile
+// Feature -> thread map inside a tile of n_feat columns: with ks = ceil(n_feat / 224) slots per thread, warp w owns the
+// 32 * ks CONSECUTIVE columns [32 ks w, 32 ks (w + 1)) and lane l evaluates columns 32 ks w + 32 k + l, k < ks.  Every warp
+// instruction still covers 32 consecutive columns (coalesced stores, one ballot = one flag word), partial tiles keep all
+// seven warps busy, and a thread's features are neighbours in the list: in an i-major all-pairs list
+// (CAVIAR-1.0.py:331) they usually share atom i, which is then loaded once.
+constexpr int kFeatStride      = 32;
 constexpr int kMaxShifts       = 16;    // lattice translations the image search may have to try
 constexpr int kRecFloats       = 12 + 4 * kMaxShifts + kMaxShifts + 12;  // 104 floats = 416 B per frame
 constexpr int kMaxStages       = 8;

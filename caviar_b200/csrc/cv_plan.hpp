@@ -210,7 +210,6 @@ inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
     const int64_t frame_bytes = 12ll * d.n_atoms;
     const int64_t u_pad_all = (hp.n_distinct + 3) / 4 * 4;
     constexpr int64_t kWholeBlockBytes = 16 * 1024;
-    const bool periodic = d.box_kind != CV_BOX_NONE;
     const bool heavy = sum_u > hp.n_distinct + hp.n_distinct / 2;
     const bool small_all = 12 * u_pad_all <= kWholeBlockBytes;
     // per-tile blocks would multiply the input bytes by more than ~8 (moderate sharing, e.g. random lists over few

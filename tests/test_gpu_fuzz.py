@@ -358,3 +358,35 @@ def test_downstream_pooled_mean_centring_and_covariance(cb):
         np.testing.assert_allclose(got.cpu().numpy(), want / len(X0), rtol=2e-4, atol=2e-5)
     with pytest.raises(TypeError):
         ds.cov_blocks(XA_ref, XA_ref)                      # host arrays: refused, no CPU path
+
+
+def test_every_combination_of_requested_outputs(cb):
+    """Any subset of {dist, flags, score} x {no aggregates, occupancy, occupancy + moments}: same values whatever else
+    is requested (a distance matrix with occupancy but WITHOUT moments once wrote through a null pointer)."""
+    import itertools
+    import torch
+    rng = np.random.default_rng(12)
+    n, T = 400, 40
+    x = torch.from_numpy((rng.random((T, n, 3)) * 30).astype(np.float32)).cuda()
+    for pairs, box in ((cb.all_pairs(n, 5), None), (rng.integers(0, n, size=(3000, 2)), "ortho")):
+        with cb.FeaturePlan(n, pairs, None, box=box, pair_cutoff=9.0) as plan:
+            rec = plan.prepare_box(torch.full((T, 3), 30.0, device="cuda")) if box else None
+            coords = plan.stage(x)
+            ref_out = plan.alloc_outputs(T)
+            ref_agg = plan.new_aggregates()
+            plan.run(coords, rec, out=ref_out, aggregates=ref_agg)
+            for r in range(0, 4):
+                for want in itertools.combinations(("dist", "flags", "score"), r):
+                    for agg_kind in (None, "occ", "all"):
+                        out = plan.alloc_outputs(T, want=want)
+                        agg = None if agg_kind is None else plan.new_aggregates(moments=agg_kind == "all")
+                        if not want and agg is None:
+                            continue
+                        plan.run(coords, rec, out=out, aggregates=agg)
+                        torch.cuda.synchronize()
+                        for name in want:
+                            assert torch.equal(getattr(out, name), getattr(ref_out, name)), (box, want, agg_kind, name)
+                        if agg is not None:
+                            assert torch.equal(agg.occupancy, ref_agg.occupancy), (box, want, agg_kind)
+                            if agg_kind == "all":
+                                assert torch.equal(agg.sum, ref_agg.sum) and torch.equal(agg.sumsq, ref_agg.sumsq)
