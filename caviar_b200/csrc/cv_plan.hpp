@@ -299,8 +299,8 @@ inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
         const int frame_b = std::max(gb + rec_b, 1);
         // Ring geometry.  Per-stage costs (barrier wait, metadata, release) are paid per warp, so few LARGE stages win:
         // two stages of as many frames as fit beat four single-frame stages by 5 % on config 3.  2 CTAs/SM when two
-        // stages of >= 1 frame fit in half of the shared memory (110 KB), else 1 CTA/SM.  CAVIAR_OCC / CAVIAR_FB
-        // override for experiments.
+        // stages of >= 1 frame fit in half of the shared memory (110 KB), else 1 CTA/SM.  CAVIAR_OCC / CAVIAR_FB /
+        // CAVIAR_STAGES override for experiments.
         int want_occ = 2;
         if (const char* e = std::getenv("CAVIAR_OCC")) want_occ = std::max(1, std::min(2, atoi(e)));
         const int budget[3] = {0, 220 * 1024, 110 * 1024};
@@ -313,6 +313,7 @@ inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
             if (f >= 1) {
                 hp.occupancy = occ; fb = f;
                 ns = std::max(2, std::min(f == 1 ? 4 : 2, room / (f * frame_b)));
+                if (const char* e = std::getenv("CAVIAR_STAGES")) ns = std::max(2, std::min(std::min(atoi(e), kMaxStages), room / (f * frame_b)));
             }
         }
         if (hp.occupancy == 0) return "a column tile's coordinate block does not fit in shared memory";

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """SASS mnemonic counts per kernel of the built library (cuobjdump -sass) + ptxas -v resource lines ->
-profiles/rNN_sass_evidence.txt.   python tools/sass_evidence.py > profiles/r01_sass_evidence.txt"""
+profiles/rNN_sass_evidence.txt.   python tools/sass_evidence.py > profiles/r02_sass_evidence.txt"""
 import os
 import re
 import subprocess
@@ -8,7 +8,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "caviar_b200", "csrc", "libcaviar_b200.so")
-COLS = [("UBLKCP", r"\bUBLKCP"), ("UBLKPF", r"\bUBLKPF"), ("SYNCS", r"\bSYNCS"), ("BAR", r"\bBAR\."),
+COLS = [("UTCHMMA", r"\bUTC[A-Z]*MMA"), ("UTMALDG", r"\bUTMALDG"), ("LDTM", r"\bLDTM"), ("UTCBAR", r"\bUTCBAR"),
+        ("UBLKCP", r"\bUBLKCP"), ("UBLKPF", r"\bUBLKPF"), ("SYNCS", r"\bSYNCS"), ("BAR", r"\bBAR\."),
         ("F*2 packed", r"\b(FFMA2|FADD2|FMUL2)\b"), ("fp64", r"\b(DFMA|DADD|DMUL)\b"), ("I2F", r"\bI2F"), ("F2F", r"\bF2F"),
         ("LDS", r"\bLDS"), ("STG", r"\bSTG")]
 sass = subprocess.run(["cuobjdump", "-sass", LIB], stdout=subprocess.PIPE, text=True).stdout
