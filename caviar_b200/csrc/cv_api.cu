@@ -780,22 +780,39 @@ extern "C" int caviar_pair_distances_host_f64(const double* xyz_host, int64_t n_
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
         return fail(CV_E_NO_DEVICE, "no CUDA device: caviar_b200 has no CPU fallback");
-    DevBuf d_pairs, d_xyz, d_out;
-    CV_CUDA(d_pairs.alloc((size_t)n_pairs * 8));
-    CV_CUDA(cudaMemcpy(d_pairs.p, pairs, (size_t)n_pairs * 8, cudaMemcpyHostToDevice));
+    // grow-only device buffers and a stream kept between calls (the operator is called once per trajectory, :337-338);
+    // blocks of frames are double-buffered: the upload of block b + 1 overlaps the kernel and download of block b
+    struct F64Ctx { std::mutex mu; DevBuf pairs, xyz[2], out[2]; Stream up, run; Event uploaded[2], done[2]; };
+    static F64Ctx* ctx = new F64Ctx();                     // never destroyed: the CUDA runtime may be gone at exit
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CV_CUDA(ctx->up.create()); CV_CUDA(ctx->run.create());
+    CV_CUDA(ctx->pairs.alloc((size_t)n_pairs * 8));
+    CV_CUDA(cudaMemcpyAsync(ctx->pairs.p, pairs, (size_t)n_pairs * 8, cudaMemcpyHostToDevice, ctx->run.s));
     const int64_t row_in = 24ll * n_atoms, row_out = 8ll * n_pairs;
-    const int64_t TB = std::max<int64_t>(1, std::min<int64_t>(n_frames, (512ll << 20) / (row_in + row_out)));
-    CV_CUDA(d_xyz.alloc((size_t)TB * row_in));
-    CV_CUDA(d_out.alloc((size_t)TB * row_out));
-    for (int64_t t0 = 0; t0 < n_frames; t0 += TB) {
+    const int64_t TB = std::max<int64_t>(1, std::min<int64_t>(n_frames, (256ll << 20) / (row_in + row_out)));
+    for (int k = 0; k < 2; ++k) {
+        CV_CUDA(ctx->xyz[k].alloc((size_t)TB * row_in)); CV_CUDA(ctx->out[k].alloc((size_t)TB * row_out));
+        CV_CUDA(ctx->uploaded[k].create()); CV_CUDA(ctx->done[k].create());
+    }
+    struct Quiesce { F64Ctx* c; ~Quiesce() { cudaStreamSynchronize(c->up.s); cudaStreamSynchronize(c->run.s); } } quiesce{ctx};
+    int64_t b = 0;
+    for (int64_t t0 = 0; t0 < n_frames; t0 += TB, ++b) {
+        const int k = (int)(b & 1);
         const int64_t n = std::min<int64_t>(TB, n_frames - t0);
-        CV_CUDA(cudaMemcpy(d_xyz.p, xyz_host + t0 * 3ll * n_atoms, (size_t)n * row_in, cudaMemcpyHostToDevice));
+        if (b >= 2) CV_CUDA(cudaStreamWaitEvent(ctx->up.s, ctx->done[k].e, 0));       // buffer set k is free again
+        CV_CUDA(cudaMemcpyAsync(ctx->xyz[k].p, xyz_host + t0 * 3ll * n_atoms, (size_t)n * row_in, cudaMemcpyHostToDevice, ctx->up.s));
+        CV_CUDA(cudaEventRecord(ctx->uploaded[k].e, ctx->up.s));
+        CV_CUDA(cudaStreamWaitEvent(ctx->run.s, ctx->uploaded[k].e, 0));
         dim3 grid((unsigned)((n_pairs + 255) / 256), (unsigned)std::min<int64_t>(n, 4096));
-        pair_distances_f64_kernel<<<grid, 256>>>(d_xyz.as<double>(), n, n_atoms, d_pairs.as<int2>(), n_pairs, d_out.as<double>());
+        pair_distances_f64_kernel<<<grid, 256, 0, ctx->run.s>>>(ctx->xyz[k].as<double>(), n, n_atoms, ctx->pairs.as<int2>(), n_pairs,
+                                                                ctx->out[k].as<double>());
         CV_CUDA(cudaGetLastError());
         g_launches += 1;
-        CV_CUDA(cudaMemcpy(dist_host + t0 * n_pairs, d_out.p, (size_t)n * row_out, cudaMemcpyDeviceToHost));
+        CV_CUDA(cudaMemcpyAsync(dist_host + t0 * n_pairs, ctx->out[k].p, (size_t)n * row_out, cudaMemcpyDeviceToHost, ctx->run.s));
+        CV_CUDA(cudaEventRecord(ctx->done[k].e, ctx->run.s));
     }
+    CV_CUDA(cudaStreamSynchronize(ctx->up.s));
+    CV_CUDA(cudaStreamSynchronize(ctx->run.s));
     return CV_OK;
 }
 

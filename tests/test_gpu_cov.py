@@ -88,3 +88,21 @@ def test_split_operand_is_exact(ds):
     assert (s.hi.view(torch.int32) & 0x1FFF).abs().max() == 0                               # hi is a TF32 number
     assert (s.hi[:, 70:] == 0).all() and (s.lo[:, 70:] == 0).all()
     assert (s.lo.abs() <= s.hi.abs() * 2.0 ** -11 + 1e-38).all()
+
+
+def test_vamp_blocks_against_the_reference_own_functions(ds, golden_dir):
+    """tests/golden/cov_blocks.npz was produced by the reference's own _stack_even_odd + _cov_blocks (cut out of
+    CAVIAR-1.0.py:396-421 with ast, unmodified, numpy float32): the tensor-core path must agree to float32 accuracy."""
+    import os
+    import torch
+    g = np.load(os.path.join(golden_dir, "cov_blocks.npz"))
+    mu = torch.from_numpy(g["mu"]).cuda()
+    ops = [ds.split_operand(torch.from_numpy(g[k]).cuda(), mu) for k in ("dist_a", "dist_b")]
+    tau = int(g["tau"])
+    for parity in (0, 1):
+        got = ds.vamp_cov_blocks(ops, tau, parity)
+        scale = max(np.diag(g[f"p{parity}_C00"]).max(), np.diag(g[f"p{parity}_Ctt"]).max())
+        for c, name in zip(got, ("C00", "Ctt", "C0t")):
+            want = g[f"p{parity}_{name}"]
+            assert c.shape == want.shape
+            assert np.abs(c.cpu().numpy() - want).max() <= 3e-6 * scale, (parity, name)      # two float32 products of the same data

@@ -434,3 +434,32 @@ def test_integration_md_ctypes_stub(cb, gold):
     assert _bits(got) == _bits(gold["C_d"])
     got = ns["compute_distances_parallel"](gold["A_x"], [(int(a), int(b)) for a, b in gold["A_pairs"]])
     assert _bits(got) == _bits(gold["A_d"])
+
+
+def test_float64_occupancy_buffer_equals_integer_occupancy(cb):
+    """Aggregates accumulated into ONE float64 buffer [occupancy | sum | sumsq] (the multi-GPU exchange buffer): the same
+    numbers as the uint64 + float64 triple, occupancy exactly integral, across several accumulating runs."""
+    import torch
+    from caviar_b200 import synthetic as syn
+    top = syn.make_topology(2, n_pairs=1500, n_triplets=300)
+    T = 200
+    pairs, triplets = syn.compact_indices(top)
+    x = torch.from_numpy(syn.parity_frames(top, T, only_referenced=True)).cuda()
+    box = torch.from_numpy(syn.boxes_for(top, T)).cuda()
+    with cb.FeaturePlan(x.shape[1], pairs, triplets, box="ortho") as plan:
+        rec = plan.prepare_box(box)
+        coords = plan.stage(x)
+        ref = plan.new_aggregates()
+        buf, packed = plan.new_packed_aggregates()
+        lean_buf, lean = plan.new_packed_aggregates(moments=False)
+        for lo, hi in ((0, 80), (80, 200)):
+            plan.run(coords[lo:hi], rec[lo:hi], aggregates=ref)
+            plan.run(coords[lo:hi], rec[lo:hi], aggregates=packed)
+            plan.run(coords[lo:hi], rec[lo:hi], out=plan.alloc_outputs(hi - lo, want=("flags",)), aggregates=lean)
+        torch.cuda.synchronize()
+        F = plan.F
+        assert buf.shape == (3 * F,) and lean_buf.shape == (F,) and buf.dtype == torch.float64
+        assert torch.equal(buf[:F], ref.occupancy.double()) and torch.equal(lean_buf, ref.occupancy.double())
+        assert torch.equal(buf[F:2 * F], ref.sum) and torch.equal(buf[2 * F:], ref.sumsq)
+        with pytest.raises(ValueError):
+            plan.run(coords, rec, aggregates=cb.Aggregates(torch.zeros(F, dtype=torch.float32, device="cuda"), None, None))

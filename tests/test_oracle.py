@@ -214,3 +214,16 @@ def test_weighted_frame_scores_are_exact_fixed_point_sums():
     perm = rng.permutation(50)
     assert np.array_equal(s, orc.weighted_frame_scores(flags[:, perm], w[perm]))       # order-independent, bit for bit
     assert np.array_equal(orc.weighted_frame_scores(flags, np.ones(50)), orc.frame_scores(flags).astype(np.float64))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/CAVIAR-1.0.py"), reason="the reference is only present in the build container")
+def test_cov_golden_is_reproducible_from_the_reference(tmp_path, golden_dir):
+    """tests/golden/cov_blocks.npz = outputs of the reference's own _cov_blocks / _stack_even_odd (cut out with ast)."""
+    import subprocess
+    import sys
+    out = tmp_path / "cov.npz"
+    subprocess.run([sys.executable, os.path.join(golden_dir, "make_cov_golden.py"), str(out)], check=True, stdout=subprocess.DEVNULL)
+    a, b = np.load(out), np.load(os.path.join(golden_dir, "cov_blocks.npz"))
+    assert sorted(a.files) == sorted(b.files)
+    for k in a.files:
+        assert a[k].tobytes() == b[k].tobytes(), k
