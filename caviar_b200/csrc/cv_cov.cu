@@ -38,17 +38,28 @@
 
 namespace cvcov {
 
-constexpr int kTileM = 128, kTileN = 128;      // C tile per CTA (= UMMA M x N)
+constexpr int kTileM = 128;                     // C tile per CTA = UMMA M x N; N is 128 or 256 (template parameter TN)
 constexpr int kBlockK = 32;                     // frames per pipeline stage (4 UMMA k-steps of 8)
 constexpr int kUmmaK = 8;                       // tf32: 32 bytes of K per instruction
 constexpr int kPanel = 32;                      // features per 128-byte swizzle row
 constexpr int kPanelBytes = kBlockK * 128;      // one [32 frames x 32 features] panel: 4 KB = 8 swizzle atoms of 4 rows x 128 B
-constexpr int kPlaneBytes = (kTileM / kPanel) * kPanelBytes;     // one operand plane of a stage: 16 KB
-constexpr int kStageBytes = 4 * kPlaneBytes;    // A.hi, A.lo, B.hi, B.lo
-constexpr int kStages = 3;
-constexpr int kTmemCols = 256;                  // two accumulators of 128 lanes x 128 float32 columns
-constexpr int kThreads = 192;                   // 6 warps
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int kPlaneBytes = (kTileM / kPanel) * kPanelBytes;     // one A plane of a stage: 16 KB (a B plane: TN / 128 times that)
+// Per tile width TN: a stage holds A.hi, A.lo (16 KB each) and B.hi, B.lo (TN / 128 x 16 KB each).  With TN = 128 every MMA
+// re-reads 4 KB of A and 4 KB of B from shared memory for 67 clocks of math -- shared-memory bandwidth (128 B/clk) and
+// the tensor core are then balanced; TN = 256 halves the A traffic per flop and is tensor-bound.
+template <int TN> struct Geo {
+    static constexpr int kBPlaneBytes = (TN / kPanel) * kPanelBytes;
+    static constexpr int kStageBytes = 2 * kPlaneBytes + 2 * kBPlaneBytes;          // 64 KB / 96 KB
+    static constexpr int kStages = TN == 128 ? 3 : 2;
+    static constexpr int kTmemCols = 2 * TN;                                        // two alternating accumulators
+    static constexpr int kEpiWarps = 4 * (TN / 128);                                // 128 accumulator columns per thread
+    static constexpr int kThreads = 64 + 32 * kEpiWarps;                            // producer + issuer + epilogue warps
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+    // Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6), A = B = TF32 [7,10) [10,13), A and B MN-major
+    // (bits 15, 16), N >> 3 at [17,23), M >> 4 at [24,29)
+    static constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                           ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -107,10 +118,6 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
     return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)(CV_LBO >> 4) << 16) | ((uint64_t)(CV_SBO >> 4) << 32) |
            (1ull << 46) | (1ull << 61);
 }
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6), A = B = TF32 [7,10) [10,13), A and B MN-major
-// (bits 15, 16), N >> 3 at [17,23), M >> 4 at [24,29)
-constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
-                                ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 
 __global__ void __launch_bounds__(256)
 cov_split_kernel(const float* __restrict__ x, long long ld_x, const float* __restrict__ mu, long long n, int K, int Kp,
@@ -158,13 +165,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // in TMEM is kept SHORT -- `flush_kblocks` stages of 32 frames -- and the partial tiles are promoted into float32
 // registers of the epilogue warps with round-to-nearest adds, exactly what a float32 sgemm does.  Two TMEM accumulators
 // alternate, so draining partial tile c overlaps the MMAs of partial tile c + 1.
-__global__ void __launch_bounds__(kThreads, 1)
+template <int TN>
+__global__ void __launch_bounds__(Geo<TN>::kThreads, 1)
 cov_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                 const GemmParams p) {
     extern __shared__ unsigned char smem_raw[];
     // swizzle atoms must sit on their natural boundaries: align the ring to 1 KB
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int kStages = Geo<TN>::kStages, kStageBytes = Geo<TN>::kStageBytes, kBPlaneBytes = Geo<TN>::kBPlaneBytes;
+    constexpr int kTmemCols = Geo<TN>::kTmemCols, kTileN = TN;
+    constexpr uint32_t kInstrDesc = Geo<TN>::kInstrDesc;
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
     uint64_t* bar_empty = bar_full + kStages;
     uint64_t* bar_acc_full = bar_empty + kStages;          // [2] partial tile complete in TMEM buffer b
@@ -179,7 +190,7 @@ cov_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(bar_acc_full + b, 1); mbar_init(bar_acc_empty + b, 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_acc_full + b, 1); mbar_init(bar_acc_empty + b, Geo<TN>::kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {            // one warp allocates the accumulator columns and later frees them
@@ -199,11 +210,11 @@ cov_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 if (kb >= kStages) mbar_wait(bar_empty + s, ((kb / kStages) - 1) & 1);
                 unsigned char* st = smem + s * kStageBytes;
                 mbar_expect_tx(bar_full + s, kStageBytes);
-                // box = {32 features, 32 frames, 4 panels}: coordinates (0, first frame, first panel)
-                tma_load_3d(st + 0 * kPlaneBytes, &map_a_hi, bar_full + s, 0, kb * kBlockK, m0 / kPanel);
-                tma_load_3d(st + 1 * kPlaneBytes, &map_a_lo, bar_full + s, 0, kb * kBlockK, m0 / kPanel);
+                // box = {32 features, 32 frames, 4 (A) or TN / 32 (B) panels}: coordinates (0, first frame, first panel)
+                tma_load_3d(st, &map_a_hi, bar_full + s, 0, kb * kBlockK, m0 / kPanel);
+                tma_load_3d(st + kPlaneBytes, &map_a_lo, bar_full + s, 0, kb * kBlockK, m0 / kPanel);
                 tma_load_3d(st + 2 * kPlaneBytes, &map_b_hi, bar_full + s, 0, kb * kBlockK, n0 / kPanel);
-                tma_load_3d(st + 3 * kPlaneBytes, &map_b_lo, bar_full + s, 0, kb * kBlockK, n0 / kPanel);
+                tma_load_3d(st + 2 * kPlaneBytes + kBPlaneBytes, &map_b_lo, bar_full + s, 0, kb * kBlockK, n0 / kPanel);
             }
         }
     } else if (warp == 1) {
@@ -223,8 +234,9 @@ cov_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 #pragma unroll
                     for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
                         // one k-step = 8 frames = two 4-row swizzle atoms: 1 KB further into every panel
-                        const uint64_t a_hi = smem_desc(base + 0 * kPlaneBytes + kk * 1024), a_lo = smem_desc(base + 1 * kPlaneBytes + kk * 1024);
-                        const uint64_t b_hi = smem_desc(base + 2 * kPlaneBytes + kk * 1024), b_lo = smem_desc(base + 3 * kPlaneBytes + kk * 1024);
+                        const uint64_t a_hi = smem_desc(base + kk * 1024), a_lo = smem_desc(base + kPlaneBytes + kk * 1024);
+                        const uint64_t b_hi = smem_desc(base + 2 * kPlaneBytes + kk * 1024);
+                        const uint64_t b_lo = smem_desc(base + 2 * kPlaneBytes + kBPlaneBytes + kk * 1024);
                         umma_tf32(tmem_d, a_lo, b_hi, kInstrDesc, first ? 0u : 1u);      // small terms first
                         umma_tf32(tmem_d, a_hi, b_lo, kInstrDesc, 1);
                         umma_tf32(tmem_d, a_hi, b_hi, kInstrDesc, 1);
@@ -238,18 +250,21 @@ cov_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     } else {
         // ===================== epilogue: TMEM -> float32 registers (promotion), then global =====================
         // a warp may only touch the TMEM lanes of its own quarter: lanes [32 * (warp % 4), + 32)
+        // (two warps share a quarter when TN = 256: each takes 128 of the accumulator's columns)
         const int q = warp & 3;
-        float acc[kTileN];
+        const int half = (warp - 2) >> 2;                  // 0 for TN = 128
+        constexpr int kCols = 128;
+        float acc[kCols];
 #pragma unroll
-        for (int j = 0; j < kTileN; ++j) acc[j] = 0.f;
+        for (int j = 0; j < kCols; ++j) acc[j] = 0.f;
         for (int c = 0; c < n_chunks; ++c) {
             const int buf = c & 1;
             mbar_wait(bar_acc_full + buf, (c >> 1) & 1);
             tcgen05_fence_after();
 #pragma unroll
-            for (int c0 = 0; c0 < kTileN; c0 += 32) {
+            for (int c0 = 0; c0 < kCols; c0 += 32) {
                 uint32_t v[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * kTileN + c0);
+                const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * kTileN + half * kCols + c0);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -268,11 +283,12 @@ cov_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         }
         const int row = m0 + 32 * q + lane;
         if (row < p.K) {
-            float* dst = p.c + (long long)row * p.ld_c + n0;
+            const int nc0 = n0 + half * kCols;
+            float* dst = p.c + (long long)row * p.ld_c + nc0;
             const bool vec = (p.ld_c & 3) == 0 && (reinterpret_cast<uintptr_t>(p.c) & 15) == 0;
 #pragma unroll
-            for (int j = 0; j < kTileN; j += 4) {
-                if (vec && n0 + j + 4 <= p.K) {
+            for (int j = 0; j < kCols; j += 4) {
+                if (vec && nc0 + j + 4 <= p.K) {
                     float4 o = p.accumulate ? *reinterpret_cast<const float4*>(dst + j) : make_float4(0.f, 0.f, 0.f, 0.f);
                     o.x = fmaf(acc[j], p.scale, o.x); o.y = fmaf(acc[j + 1], p.scale, o.y);
                     o.z = fmaf(acc[j + 2], p.scale, o.z); o.w = fmaf(acc[j + 3], p.scale, o.w);
@@ -280,7 +296,7 @@ cov_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 } else {
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        if (n0 + j + i < p.K) dst[j + i] = fmaf(acc[j + i], p.scale, p.accumulate ? dst[j + i] : 0.f);
+                        if (nc0 + j + i < p.K) dst[j + i] = fmaf(acc[j + i], p.scale, p.accumulate ? dst[j + i] : 0.f);
                 }
             }
         }
@@ -312,12 +328,12 @@ static EncodeTiledFn encode_fn() {
 
 // (n, Kp) row-major float32 plane seen as {32 features, n frames, Kp / 32 panels}: a box {32, 32, 4} lands in shared
 // memory panel by panel, each panel 32 rows of 128 bytes, 128-byte swizzled -- the canonical MN-major UMMA operand.
-static bool make_map(CUtensorMap* map, const float* plane, long long n, long long row_stride_floats, int Kp) {
+static bool make_map(CUtensorMap* map, const float* plane, long long n, long long row_stride_floats, int Kp, int box_panels) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     const cuuint64_t dims[3] = {(cuuint64_t)kPanel, (cuuint64_t)n, (cuuint64_t)(Kp / kPanel)};
     const cuuint64_t strides[2] = {(cuuint64_t)row_stride_floats * 4, (cuuint64_t)kPanel * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)kPanel, (cuuint32_t)kBlockK, (cuuint32_t)(kTileM / kPanel)};
+    const cuuint32_t box[3] = {(cuuint32_t)kPanel, (cuuint32_t)kBlockK, (cuuint32_t)box_panels};
     const cuuint32_t estr[3] = {1, 1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(plane), dims, strides, box, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -361,14 +377,21 @@ extern "C" int caviar_cov_gemm(const float* a_hi_dev, const float* a_lo_dev, con
         return caviar_set_error(CV_E_INVALID, "cov_gemm: planes must be 16-byte aligned");
     if (n_rows >= (1ll << 31)) return caviar_set_error(CV_E_INVALID, "cov_gemm: too many rows");
     const int Kp = (int)caviar_cov_padded_columns(n_cols);
+    // 128 x 256 tiles (tensor-bound) when C is wide enough to fill the SMs with them, else 128 x 128; CAVIAR_COV_TILE_N overrides
+    static const int forced_tn = [] { const char* e = getenv("CAVIAR_COV_TILE_N"); return e ? atoi(e) : 0; }();
+    const int tn = forced_tn == 128 || forced_tn == 256 ? forced_tn : ((long long)(Kp / 256) * (Kp / 128) >= 148 ? 256 : 128);
     CUtensorMap maps[4];
     const float* planes[4] = {a_hi_dev, a_lo_dev, b_hi_dev, b_lo_dev};
     for (int i = 0; i < 4; ++i)
-        if (!make_map(&maps[i], planes[i], n_rows, row_stride_floats, Kp))
+        if (!make_map(&maps[i], planes[i], n_rows, row_stride_floats, Kp, i < 2 ? kTileM / kPanel : tn / kPanel))
             return caviar_set_error(CV_E_CUDA, "cov_gemm: cuTensorMapEncodeTiled failed (driver entry point missing or bad plane)");
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(cov_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes); });
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(cov_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<128>::kSmemBytes);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(cov_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<256>::kSmemBytes);
+    });
     if (attr_err != cudaSuccess) return caviar_set_error(CV_E_CUDA, cudaGetErrorString(attr_err));
     GemmParams p;
     p.n = n_rows; p.K = (int)n_cols; p.ld_c = ld_c; p.scale = scale; p.accumulate = accumulate ? 1 : 0; p.c = c_dev;
@@ -377,8 +400,13 @@ extern "C" int caviar_cov_gemm(const float* a_hi_dev, const float* a_lo_dev, con
     // 4 -> 1.5e-6 / 1.96 ms, 8 -> 2.5e-6 / 1.89 ms, 64 -> 2.1e-5 / 1.82 ms; cuBLAS float32 6.8e-6 / 7.85 ms, TF32 1.1e-4.
     static const int flush = [] { const char* e = getenv("CAVIAR_COV_FLUSH"); return std::max(1, e ? atoi(e) : 4); }();
     p.flush_kblocks = flush;
-    dim3 grid(Kp / kTileN, Kp / kTileM);
-    cov_gemm_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+    if (tn == 256) {
+        dim3 grid((Kp + 255) / 256, Kp / kTileM);
+        cov_gemm_kernel<256><<<grid, Geo<256>::kThreads, Geo<256>::kSmemBytes, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+    } else {
+        dim3 grid(Kp / 128, Kp / kTileM);
+        cov_gemm_kernel<128><<<grid, Geo<128>::kThreads, Geo<128>::kSmemBytes, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return caviar_set_error(CV_E_CUDA, cudaGetErrorString(e));
     return CV_OK;
