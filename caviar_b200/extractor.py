@@ -176,7 +176,7 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
 
     labels = read_pairs(args.pairs or "", args.pairs_file or "")
     top = trajio.read_topology(args.top)
-    traj = trajio.Trajectory(args.traj)
+    traj = trajio.Trajectory(args.traj, n_atoms=top.n_atoms)
     if traj.n_atoms != top.n_atoms:
         sys.exit(f"[ERR] topologia ({top.n_atoms} atomi) e traiettoria ({traj.n_atoms} atomi) non corrispondono")
     pair_atoms = select_atoms(top, labels, args.numbering, args.offset)

@@ -236,12 +236,22 @@ def cell_to_matrix(lengths: np.ndarray, angles_deg: np.ndarray) -> np.ndarray:
 class Trajectory:
     """Random access to frame blocks: ``coords(lo, hi, stride)`` -> float32 (n, N, 3); ``cell(...)`` -> box or None."""
 
-    def __init__(self, path: str):
+    def __init__(self, path: str, n_atoms: Optional[int] = None):
+        """``n_atoms`` is only needed for formats that do not record it (Amber ASCII mdcrd): pass the topology's."""
         self.path = path
         ext = os.path.splitext(path)[1].lower()
         self._nc = None
         self._dcd = None
         self._trr = None
+        self._crd = None
+        if ext in (".mdcrd", ".crd", ".trj"):
+            if not n_atoms:
+                sys.exit("[ERR] una traiettoria Amber ASCII (mdcrd) non contiene il numero di atomi: serve la topologia")
+            self._crd = _MdcrdFile(path, int(n_atoms))
+            self._xyz = None
+            self._len = self._ang = None
+            self.n_frames, self.n_atoms = self._crd.n_frames, self._crd.n_atoms
+            return
         if ext == ".trr":
             self._trr = _TrrFile(path)
             self._xyz = None
@@ -269,11 +279,9 @@ class Trajectory:
                     what = "NetCDF-4 / HDF5 (convert with `cpptraj` or `ncks -3` to NetCDF-3, the Amber convention)"
                 elif ext == ".xtc":
                     what = "GROMACS XTC (compressed coordinates are not read; convert to .trr, .dcd or .nc)"
-                elif ext in (".mdcrd", ".crd", ".trj"):
-                    what = "Amber ASCII mdcrd (not read; convert to .nc)"
                 else:
                     what = f"unknown format '{ext or path}'"
-                sys.exit(f"[ERR] formato di traiettoria non supportato: {what}. Supportati: Amber NetCDF-3 (.nc), DCD, TRR, .npy")
+                sys.exit(f"[ERR] formato di traiettoria non supportato: {what}. Supportati: Amber NetCDF-3 (.nc), mdcrd, DCD, TRR, .npy")
             from scipy.io import netcdf_file
             self._nc = netcdf_file(path, "r", mmap=True)
             if "coordinates" not in self._nc.variables:
@@ -285,6 +293,8 @@ class Trajectory:
 
     @property
     def has_box(self) -> bool:
+        if self._crd is not None:
+            return self._crd.has_box
         if self._trr is not None:
             return self._trr.has_box and self.n_frames > 0 and bool(np.all(np.diag(self._trr.box(0, 1)[0]) > 0))
         if self._dcd is not None:
@@ -296,6 +306,8 @@ class Trajectory:
     def box_kind(self) -> Optional[str]:
         if not self.has_box:
             return None
+        if self._crd is not None:
+            return "ortho"                                        # an mdcrd box line holds the three edge lengths only
         if self._trr is not None:
             h = self._trr.box(0, 1)[0]
             off = np.abs(h - np.diag(np.diag(h))).max()
@@ -304,6 +316,8 @@ class Trajectory:
         return "ortho" if np.allclose(ang, 90.0, atol=1e-6) else "triclinic"
 
     def coords(self, lo: int, hi: int, stride: int = 1) -> np.ndarray:
+        if self._crd is not None:
+            return self._crd.coords(lo, hi, stride)
         if self._dcd is not None or self._trr is not None:
             return self.coords_of(np.arange(self.n_atoms), lo, hi, stride)
         return np.ascontiguousarray(self._xyz[lo:hi:stride], dtype=np.float32)
@@ -318,6 +332,9 @@ class Trajectory:
         n = len(range(lo, hi, stride))
         if out is None:
             out = np.empty((n, len(atoms), 3), dtype=np.float32)
+        if self._crd is not None:                                  # text: parse the frames, then pick the atoms
+            out[...] = self._crd.coords(lo, hi, stride)[:, atoms, :]
+            return out
         if self._trr is not None:
             if n and len(atoms):
                 r = self._trr
@@ -348,6 +365,8 @@ class Trajectory:
         kind = self.box_kind()
         if kind is None:
             return None
+        if self._crd is not None:
+            return self._crd.box(lo, hi, stride)
         if self._trr is not None:
             h = self._trr.box(lo, hi, stride) * 10.0                 # nm -> Angstrom; rows = box vectors (a along x)
             return np.stack([h[:, 0, 0], h[:, 1, 1], h[:, 2, 2]], axis=1).astype(np.float32) if kind == "ortho" \
@@ -362,6 +381,9 @@ class Trajectory:
         return cell_to_matrix(L, A).astype(np.float32)
 
     def close(self):
+        if self._crd is not None:
+            self._crd.close()
+            self._crd = None
         if self._trr is not None:
             self._trr.close()
             self._trr = None
@@ -375,6 +397,69 @@ class Trajectory:
             except Exception:
                 pass
             self._nc = None
+
+
+class _MdcrdFile:
+    """Amber ASCII trajectory (mdcrd): a title line, then per frame 3N coordinates in Fortran 10F8.3 (eight characters
+    per value, ten per line, no separator guaranteed) and, for periodic runs, one more line with the three box lengths.
+    The file records neither N nor whether it has box lines: N comes from the topology, the box is inferred from the
+    file size (every frame has the same number of bytes).  Frames are parsed on demand from a read-only memory map."""
+
+    def __init__(self, path: str, n_atoms: int):
+        self._mm = np.memmap(path, dtype=np.uint8, mode="r")
+        mm = self._mm
+        self.n_atoms = n_atoms
+        nl = int(np.flatnonzero(mm[:4096] == 10)[0]) if (mm[:4096] == 10).any() else -1
+        if nl < 0:
+            raise ValueError(f"{path}: no title line (not an Amber mdcrd file)")
+        self.first = nl + 1
+        n_val = 3 * n_atoms
+        lines = (n_val + 9) // 10
+        eol = 2 if nl > 0 and mm[nl - 1] == 13 else 1                 # CR LF files exist
+        self.eol = eol
+        self.coord_bytes = 8 * n_val + eol * lines
+        body = mm.size - self.first
+        box_bytes = 24 + eol
+        if body % self.coord_bytes == 0 and body % (self.coord_bytes + box_bytes) != 0:
+            self.has_box = False
+        elif body % (self.coord_bytes + box_bytes) == 0:
+            # both divide only for contrived sizes: then look whether the line after the first frame is a 3-value line
+            self.has_box = body % self.coord_bytes != 0 or self._line_len(self.first + self.coord_bytes) == 24
+        else:
+            raise ValueError(f"{path}: file size does not match {n_atoms} atoms (with or without box lines)")
+        self.frame_bytes = self.coord_bytes + (box_bytes if self.has_box else 0)
+        self.n_frames = body // self.frame_bytes
+        # positions of the value characters inside one frame's coordinate block (newlines skipped)
+        k = np.arange(8 * n_val, dtype=np.int64)
+        self._pos = k + (k // 80) * eol
+
+    def _line_len(self, pos: int) -> int:
+        seg = self._mm[pos:pos + 200]
+        nl = np.flatnonzero(seg == 10)
+        return int(nl[0]) - (self.eol - 1) if len(nl) else -1
+
+    def _numbers(self, raw: np.ndarray) -> np.ndarray:
+        return np.char.strip(raw.view("S8")).astype(np.float64)
+
+    def coords(self, lo: int, hi: int, stride: int = 1) -> np.ndarray:
+        idx = np.arange(lo, hi, max(1, stride))
+        out = np.empty((len(idx), self.n_atoms, 3), dtype=np.float32)
+        for k, t in enumerate(idx):
+            o = self.first + int(t) * self.frame_bytes
+            block = np.asarray(self._mm[o:o + self.coord_bytes])
+            out[k] = self._numbers(np.ascontiguousarray(block[self._pos])).reshape(self.n_atoms, 3)
+        return out
+
+    def box(self, lo: int, hi: int, stride: int = 1) -> np.ndarray:
+        idx = np.arange(lo, hi, max(1, stride))
+        out = np.empty((len(idx), 3), dtype=np.float32)
+        for k, t in enumerate(idx):
+            o = self.first + int(t) * self.frame_bytes + self.coord_bytes
+            out[k] = self._numbers(np.ascontiguousarray(np.asarray(self._mm[o:o + 24])))
+        return out
+
+    def close(self):
+        self._mm = None
 
 
 class _TrrFile:

@@ -312,7 +312,7 @@ def test_unsupported_inputs_fail_with_a_clear_message(ext, tmp_path):
     """The formats the reference's help text lists but this reader does not take (Extractor:99) exit with [ERR],
     not with a scipy traceback; resSeq numbering needs a topology that carries residue numbers."""
     from caviar_b200 import trajio
-    for name, head in (("t.xtc", b"\x00\x00\x07\xcb" + b"\0" * 60), ("t.mdcrd", b"title\n  1.000  2.000\n"),
+    for name, head in (("t.xtc", b"\x00\x00\x07\xcb" + b"\0" * 60),
                        ("t4.nc", b"\x89HDF\r\n\x1a\n" + b"\0" * 60), ("t.foo", b"whatever")):
         p = tmp_path / name
         p.write_bytes(head)

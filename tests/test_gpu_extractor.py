@@ -123,3 +123,35 @@ def test_drop_in_reproduces_the_reference_main_byte_for_byte(tmp_path, capsys, g
         printed = capsys.readouterr().out
         assert open(work / out, "rb").read() == open(os.path.join(gdir, c["csv"]), "rb").read(), c["name"]
         assert printed.replace(out, c["csv"]) == open(os.path.join(gdir, c["stdout"])).read(), c["name"]
+
+
+def test_extractor_reads_amber_ascii_mdcrd(tmp_path, capsys, golden_dir):
+    """The formats the reference's help text names (Extractor:99): an Amber ASCII trajectory (10F8.3, box line per frame)
+    written here by hand goes through the drop-in; distances against the oracle on the 3-decimal coordinates."""
+    import os
+    from scipy.io import netcdf_file
+    from caviar_b200 import extractor
+    gdir = os.path.join(golden_dir, "extractor")
+    nc = netcdf_file(os.path.join(gdir, "traj_ortho.nc"), "r", mmap=False)
+    xyz = np.round(np.array(nc.variables["coordinates"][:], dtype=np.float64), 3)
+    box = np.round(np.array(nc.variables["cell_lengths"][:], dtype=np.float64), 3)
+    nc.close()
+    text = "converted from traj_ortho.nc\n"
+    for t in range(xyz.shape[0]):
+        vals = xyz[t].ravel()
+        for k in range(0, len(vals), 10):
+            text += "".join("%8.3f" % v for v in vals[k:k + 10]) + "\n"
+        text += "".join("%8.3f" % v for v in box[t]) + "\n"
+    crd = tmp_path / "traj.mdcrd"
+    crd.write_text(text)
+    out = tmp_path / "out.csv"
+    assert extractor.main(["--top", os.path.join(gdir, "sys.prmtop"), "--traj", str(crd), "--pairs", "ASP1-SER5,GLY4-LEU27",
+                           "--out", str(out)]) == 0
+    capsys.readouterr()
+    with open(out, newline="") as fh:
+        table = list(csv.reader(fh))
+    assert table[0] == ["#Frame", "ASP1-SER5", "GLY4-LEU27"] and len(table) == 1 + xyz.shape[0]
+    got = np.array([[float(v) for v in r[1:]] for r in table[1:]])
+    ca = lambda r: 4 * r + 1
+    want = orc.pbc_pair_distances(xyz.astype(np.float32), [(ca(0), ca(4)), (ca(3), ca(26))], box.astype(np.float32))
+    assert np.abs(got - want).max() <= 1e-4 + 0.5e-4

@@ -136,3 +136,41 @@ def test_trr_assembled_from_the_format_description(trajio, tmp_path, vp, v, f):
     tr = trajio.Trajectory(str(p3))
     assert tr.box_kind() == "ortho" and np.allclose(tr.cell(0, T), [[30.0, 40.0, 50.0]] * T)
     tr.close()
+
+
+def _mdcrd(xyz, box=None, eol="\n"):
+    out = "extractor test trajectory" + eol
+    for t in range(xyz.shape[0]):
+        vals = xyz[t].ravel()
+        for k in range(0, len(vals), 10):
+            out += "".join("%8.3f" % v for v in vals[k:k + 10]) + eol
+        if box is not None:
+            out += "".join("%8.3f" % v for v in box[t]) + eol
+    return out.encode()
+
+
+@pytest.mark.parametrize("n,with_box,eol", [(37, True, "\n"), (40, False, "\n"), (11, True, "\r\n"), (1, True, "\n")])
+def test_mdcrd_assembled_from_the_format_description(trajio, tmp_path, n, with_box, eol):
+    """Amber ASCII trajectory: title, 10F8.3 coordinate lines (values may touch: '-123.456-234.567'), optional box line;
+    the atom count comes from the topology."""
+    T = 6
+    xyz = np.round(_coords(T, n) - 300.0, 3).astype(np.float32)          # negative, touching fields
+    box = [(40.0 + t, 41.125, 39.5) for t in range(T)] if with_box else None
+    p = tmp_path / "foreign.mdcrd"
+    p.write_bytes(_mdcrd(xyz, box, eol))
+    tr = trajio.Trajectory(str(p), n_atoms=n)
+    assert (tr.n_frames, tr.n_atoms) == (T, n)
+    np.testing.assert_allclose(tr.coords(0, T), xyz, rtol=0, atol=6e-5)
+    np.testing.assert_allclose(tr.coords(1, T, 2), xyz[1:T:2], rtol=0, atol=6e-5)
+    sel = np.array([n - 1, 0, 0], dtype=np.int32)
+    np.testing.assert_allclose(tr.coords_of(sel, 0, T), xyz[:, sel, :], rtol=0, atol=6e-5)
+    if with_box:
+        assert tr.box_kind() == "ortho"
+        np.testing.assert_allclose(tr.cell(0, T), np.array(box, dtype=np.float32), atol=1e-3)
+    else:
+        assert tr.box_kind() is None and tr.cell(0, T) is None
+    tr.close()
+    with pytest.raises(SystemExit):
+        trajio.Trajectory(str(p))                                        # no atom count, no guess
+    with pytest.raises(ValueError):
+        trajio.Trajectory(str(p), n_atoms=n + 1)
