@@ -19,9 +19,9 @@ class CaviarError(RuntimeError):
 CV_OK, CV_E_INVALID, CV_E_CUDA, CV_E_NO_DEVICE, CV_E_UNSUPPORTED, CV_E_NOMEM = 0, -1, -2, -3, -4, -5
 BOX_NONE, BOX_ORTHO, BOX_TRICLINIC = 0, 1, 2
 PLAN_FORCE_DIRECT, PLAN_FORCE_STAGED = 1, 2
-MODE_DIRECT, MODE_ZEROCOPY, MODE_STAGED = 0, 1, 2
+MODE_DIRECT, MODE_ZEROCOPY, MODE_STAGED, MODE_ALLPAIRS = 0, 1, 2, 3
 ORDER_CALLER, ORDER_PLAN = 0, 1
-MODE_NAMES = {MODE_DIRECT: "direct", MODE_ZEROCOPY: "zerocopy", MODE_STAGED: "staged"}
+MODE_NAMES = {MODE_DIRECT: "direct", MODE_ZEROCOPY: "zerocopy", MODE_STAGED: "staged", MODE_ALLPAIRS: "allpairs"}
 
 
 class CvPlanDesc(C.Structure):
@@ -70,6 +70,7 @@ class CvHostOutputs(C.Structure):
 SYMBOLS = {
     "caviar_plan_describe": (C.c_int, [C.POINTER(CvPlanDesc), C.c_int32, C.POINTER(CvPlanInfo)]),
     "caviar_plan_layout": (C.c_int, [C.POINTER(CvPlanDesc), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "caviar_plan_allpairs_check": (C.c_int64, [C.POINTER(CvPlanDesc), C.c_int32, C.c_void_p]),
     "caviar_plan_create": (C.c_int, [C.POINTER(CvPlanDesc), C.POINTER(C.c_void_p)]),
     "caviar_plan_destroy": (None, [C.c_void_p]),
     "caviar_plan_info": (C.c_int, [C.c_void_p, C.POINTER(CvPlanInfo)]),

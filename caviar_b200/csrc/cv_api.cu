@@ -14,6 +14,7 @@
 
 #include "../../include/caviar_b200.h"
 #include "cv_device.cuh"
+#include "cv_allpairs.cuh"
 #include "cv_plan.hpp"
 
 using namespace cv;
@@ -141,6 +142,8 @@ struct CvPlan {
     int32_t *d_idx0 = nullptr, *d_idx1 = nullptr, *d_idx2 = nullptr;
     int32_t* d_src_off = nullptr;
     int32_t* d_pairs = nullptr;        // [P][2] in the caller's numbering, uploaded on first use (caviar_residue_components)
+    ApTile* d_ap_tiles = nullptr;      // all-pairs flavour (hp.ap.on): tiles, row of every flag word, first pair of every row
+    int32_t *d_ap_row_of_word = nullptr, *d_ap_row_off = nullptr;
     int* d_err = nullptr;
     mutable HostCtx host;     // cached resources of the host entry point
 };
@@ -164,6 +167,7 @@ extern "C" int caviar_plan_layout(const CvPlanDesc* desc, int32_t n_sms, int32_t
     HostPlan hp;
     std::string why = build_plan(*desc, n_sms, hp);
     if (!why.empty()) return fail(CV_E_INVALID, why);
+    if (hp.ap.on) return fail(CV_E_INVALID, "all-pairs plans keep no index tables: caviar_plan_allpairs_check verifies their geometry");
     const size_t C = hp.tiles.size();
     if (tile_desc)
         for (size_t c = 0; c < C; ++c) {
@@ -180,6 +184,72 @@ extern "C" int caviar_plan_layout(const CvPlanDesc* desc, int32_t n_sms, int32_t
     return CV_OK;
 }
 
+
+// Host-side check of the all-pairs geometry (no GPU): runs the kernel's own per-thread set-up (ap_thread_setup) for
+// every tile, warp and lane and verifies that every pair of the list is evaluated exactly once, that the shared-memory
+// offsets resolve to the pair's atoms inside the tile's atom ranges, that fast warps really are warp-uniform in i and
+// affine in j, and that the TMA alignment rules hold.  Returns the number of tiles (0: the plan does not use the
+// all-pairs flavour), < 0 on a violation (caviar_last_error says which).
+//   stats (optional, 8 values): windows, fast windows, largest tile block in atoms, frames per stage, stages,
+//   shared-memory bytes, mean atoms per tile, CTAs
+extern "C" int64_t caviar_plan_allpairs_check(const CvPlanDesc* desc, int32_t n_sms, int64_t* stats) {
+    if (!desc) return fail(CV_E_INVALID, "null argument");
+    HostPlan hp;
+    std::string why = build_plan(*desc, n_sms, hp);
+    if (!why.empty()) return fail(CV_E_INVALID, why);
+    const ApHost& ap = hp.ap;
+    if (stats) for (int q = 0; q < 8; ++q) stats[q] = 0;
+    if (!ap.on) return 0;
+    const int64_t P = hp.P;
+    const int n = hp.desc.n_atoms;
+    std::vector<uint8_t> seen((size_t)P, 0);
+    int64_t max_atoms = 0, sum_atoms = 0;
+    for (size_t c = 0; c < ap.tiles.size(); ++c) {
+        const ApTile& t = ap.tiles[c];
+        const std::string at = " (tile " + std::to_string(c) + ")";
+        if (t.a0 % 4 || t.n0 % 4 || t.a1 % 4 || t.n1 % 4 || t.n0 < 4 || t.a0 < 0 || t.a0 + t.n0 > n) return fail(CV_E_INVALID, "atom range 0 misaligned or out of the frame" + at);
+        if (t.n1 > 0 && (t.a1 < t.a0 + t.n0 || t.a1 + t.n1 > n)) return fail(CV_E_INVALID, "atom range 1 overlaps range 0 or leaves the frame" + at);
+        if (3 * (t.n0 + t.n1) * ap.frames_per_stage > ap.stage_floats) return fail(CV_E_INVALID, "stage too small" + at);
+        max_atoms = std::max<int64_t>(max_atoms, t.n0 + t.n1); sum_atoms += t.n0 + t.n1;
+        if (getenv("CAVIAR_AP_DUMP") && t.n0 + t.n1 > atoi(getenv("CAVIAR_AP_DUMP")))
+            fprintf(stderr, "tile %zu fast_mask %x atoms [%d,+%d) [%d,+%d) blk0 %d..%d blk1 %d..%d\n", c, t.fast_mask, t.a0, t.n0, t.a1, t.n1,
+                    t.blk[0][0], t.blk[0][6], t.blk[1][0], t.blk[1][6]);
+        auto atom_of = [&](int off) { const int a = off / 3; return a < t.n0 ? t.a0 + a : t.a1 + (a - t.n0); };
+        for (int w = 0; w < kApWarps; ++w) {
+            const bool fast = (t.fast_mask >> w) & 1;
+            int i_uniform[2] = {-1, -1};
+            for (int lane = 0; lane < 32; ++lane) {
+                ApThread th;
+                ap_thread_setup(t, w, lane, ap.row_of_word.data(), ap.row_off.data(), ap.minsep, P, th);
+                if (fast && th.vmask != 0xFFu) return fail(CV_E_INVALID, "fast warp with a missing slot" + at);
+                for (int q = 0; q < 2 * kApSlots; ++q) {
+                    if (!((th.vmask >> q) & 1u)) continue;
+                    const int win = q / kApSlots, m = q % kApSlots;
+                    const int64_t k = (int64_t)th.kbase[win] + 32 * m + lane;
+                    if (k < 0 || k >= P) return fail(CV_E_INVALID, "slot beyond the list" + at);
+                    if (seen[k]++) return fail(CV_E_INVALID, "pair " + std::to_string(k) + " evaluated twice" + at);
+                    int io = th.ioff[q], jo = th.joff[q];
+                    if (fast) {                       // what ap_fast_frame reads
+                        io = th.ioff[kApSlots * win]; jo = th.joff[kApSlots * win] + 96 * m;
+                        if (i_uniform[win] < 0) i_uniform[win] = io;
+                        if (io != i_uniform[win]) return fail(CV_E_INVALID, "fast warp is not uniform in i" + at);
+                    }
+                    if (io < 0 || jo < 0 || io % 3 || jo % 3 || io / 3 >= t.n0 + t.n1 || jo / 3 >= t.n0 + t.n1)
+                        return fail(CV_E_INVALID, "offset outside the tile's block" + at);
+                    if (atom_of(io) != hp.pairs[2 * k] || atom_of(jo) != hp.pairs[2 * k + 1])
+                        return fail(CV_E_INVALID, "pair " + std::to_string(k) + " resolves to the wrong atoms" + at);
+                }
+            }
+        }
+    }
+    for (int64_t k = 0; k < P; ++k) if (!seen[k]) return fail(CV_E_INVALID, "pair " + std::to_string(k) + " is never evaluated");
+    if (stats) {
+        stats[0] = ap.n_windows; stats[1] = ap.n_fast_windows; stats[2] = max_atoms; stats[3] = ap.frames_per_stage;
+        stats[4] = ap.n_stages; stats[5] = ap.smem_bytes; stats[6] = sum_atoms / (int64_t)ap.tiles.size(); stats[7] = ap.n_ctas;
+    }
+    return (int64_t)ap.tiles.size();
+}
+
 template <typename T>
 static cudaError_t upload(T** dst, const std::vector<T>& src) {
     *dst = nullptr;
@@ -194,6 +264,7 @@ extern "C" void caviar_plan_destroy(CvPlan* plan) {
     cudaFree(plan->d_tiles);
     cudaFree(plan->d_idx0); cudaFree(plan->d_idx1); cudaFree(plan->d_idx2);
     cudaFree(plan->d_src_off); cudaFree(plan->d_err); cudaFree(plan->d_pairs);
+    cudaFree(plan->d_ap_tiles); cudaFree(plan->d_ap_row_of_word); cudaFree(plan->d_ap_row_off);
     delete plan;
 }
 
@@ -221,6 +292,9 @@ extern "C" int caviar_plan_create(const CvPlanDesc* desc, CvPlan** out) {
     if (e == cudaSuccess) e = upload(&p->d_idx1, p->hp.idx1);
     if (e == cudaSuccess) e = upload(&p->d_idx2, p->hp.idx2);
     if (e == cudaSuccess) e = upload(&p->d_src_off, p->hp.src_off);
+    if (e == cudaSuccess && p->hp.ap.on) e = upload(&p->d_ap_tiles, p->hp.ap.tiles);
+    if (e == cudaSuccess && p->hp.ap.on) e = upload(&p->d_ap_row_of_word, p->hp.ap.row_of_word);
+    if (e == cudaSuccess && p->hp.ap.on) e = upload(&p->d_ap_row_off, p->hp.ap.row_off);
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_err, sizeof(int));          // box set-up errors
     if (e == cudaSuccess) e = cudaMemset(p->d_err, 0, sizeof(int));
     if (e != cudaSuccess) {
@@ -325,6 +399,50 @@ static cudaError_t launch_features(const CvPlan* plan, const RunParams& rp, cuda
     return cudaGetLastError();
 }
 
+
+template <bool LEAN, bool FAST>
+static cudaError_t launch_allpairs(const CvPlan* plan, const ApParams& ap, cudaStream_t st) {
+    if (ap.n_tiles <= 0) return cudaSuccess;
+    auto kern = allpairs_kernel<LEAN, FAST>;
+    const int smem = plan->hp.ap.smem_bytes;
+    static int granted[64] = {0};
+    const int dev = plan->device & 63;
+    if (smem > granted[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        granted[dev] = smem;
+    }
+    kern<<<plan->hp.ap.n_ctas, kConsumerThreads + kProducerThreads, smem, st>>>(ap);
+    return cudaGetLastError();
+}
+
+// Frame chunks of the work queue: about kItemsPerCta items per CTA, whole pipeline stages each.  The last
+// quarter of the frames is cut into chunks a quarter the size, so that the CTAs run dry within a quarter item
+// of each other (the queue is chunk-major: small chunks are handed out last).
+struct Chunking { int32_t chunk_frames, tail_frames, n_big_chunks, n_chunks; };
+static bool make_chunks(int64_t n_frames, int64_t fb, int max_chunks, int64_t n_tiles, int n_ctas, Chunking& c) {
+    const int64_t unit = 4 * fb;
+    int64_t cf = std::max<int64_t>((7 * n_frames / 4 + max_chunks - 1) / max_chunks, kMinChunkFrames);
+    cf = std::max<int64_t>(unit, (cf + unit - 1) / unit * unit);
+    if (cf > (1ll << 30)) return false;
+    const int64_t tf = cf / 4;
+    int64_t n_big = (3 * n_frames / 4) / cf;
+    int64_t n_small = (n_frames - n_big * cf + tf - 1) / tf;
+    // Short runs (tail items below kMinChunkFrames frames): every item costs a flush of 24 B per feature and a
+    // pipeline restart, so the small tail only pays when a CTA gets so few items that imbalance dominates
+    // (config 2: 4 items per CTA, +4 %; config 5 at 4 096 frames: 16 per CTA, -3.5 % -> uniform chunks there).
+    const int64_t uniform_items = (n_frames + cf - 1) / cf * n_tiles;
+    const bool small_tail_pays = uniform_items < 8ll * n_ctas;
+    if (tf < kMinTailFrames || (tf < kMinChunkFrames && !small_tail_pays) || n_big + n_small > max_chunks) {
+        n_big = (n_frames + cf - 1) / cf; n_small = 0;
+    }
+    c.chunk_frames = (int32_t)cf;
+    c.tail_frames = (int32_t)tf;
+    c.n_big_chunks = (int32_t)n_big;
+    c.n_chunks = (int32_t)(n_big + n_small);
+    return true;
+}
+
 extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t frame_stride_floats,
                           const float* boxrec_dev, int64_t n_frames, const CvFrameOutputs* out,
                           const CvAggregates* agg, void* workspace_dev, void* stream) {
@@ -361,7 +479,7 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
             return fail(CV_E_INVALID, "plan-order frames: stride must be >= staged_floats_per_frame and a multiple of 4 floats");
     } else {
         if (frame_stride_floats < 3ll * hp.desc.n_atoms) return fail(CV_E_INVALID, "frame stride smaller than 3*n_atoms");
-        if (hp.mode == CV_MODE_ZEROCOPY && frame_stride_floats != 3ll * hp.desc.n_atoms)
+        if (hp.mode == CV_MODE_ZEROCOPY && frame_stride_floats != 3ll * hp.desc.n_atoms && !(hp.ap.on && frame_stride_floats % 4 == 0))
             return fail(CV_E_INVALID, "zero-copy mode needs densely packed frames (stride == 3*n_atoms)");
         rp.frame_stride = frame_stride_floats;
     }
@@ -377,31 +495,14 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
     if (out) { rp.dist = out->dist; rp.angle = out->angle; rp.flags = out->flags; rp.score = out->score; }
     rp.P = hp.P; rp.A = hp.A; rp.W = hp.W; rp.Wp = hp.Wp;
     const long long F = hp.P + hp.A;
-    // Frame chunks of the work queue: about kItemsPerCta items per CTA, whole pipeline stages each.  The last
-    // quarter of the frames is cut into chunks a quarter the size, so that the CTAs run dry within a quarter item
-    // of each other (the queue is chunk-major: small chunks are handed out last).
-    {
-        const int64_t fb = hp.frames_per_stage;
-        const int64_t unit = 4 * fb;
-        int64_t cf = std::max<int64_t>((7 * n_frames / 4 + hp.max_chunks - 1) / hp.max_chunks, kMinChunkFrames);
-        cf = std::max<int64_t>(unit, (cf + unit - 1) / unit * unit);
-        if (cf > (1ll << 30)) return fail(CV_E_INVALID, "too many frames for one run: split the call");
-        const int64_t tf = cf / 4;
-        int64_t n_big = (3 * n_frames / 4) / cf;
-        int64_t n_small = (n_frames - n_big * cf + tf - 1) / tf;
-        // Short runs (tail items below kMinChunkFrames frames): every item costs a flush of 24 B per feature and a
-        // pipeline restart, so the small tail only pays when a CTA gets so few items that imbalance dominates
-        // (config 2: 4 items per CTA, +4 %; config 5 at 4 096 frames: 16 per CTA, -3.5 % -> uniform chunks there).
-        const int64_t uniform_items = (n_frames + cf - 1) / cf * (int64_t)hp.tiles.size();
-        const bool small_tail_pays = uniform_items < 8ll * hp.n_ctas;
-        if (tf < kMinTailFrames || (tf < kMinChunkFrames && !small_tail_pays) || n_big + n_small > hp.max_chunks) {
-            n_big = (n_frames + cf - 1) / cf; n_small = 0;
-        }
-        rp.chunk_frames = (int32_t)cf;
-        rp.tail_frames = (int32_t)tf;
-        rp.n_big_chunks = (int32_t)n_big;
-        rp.n_chunks = (int32_t)(n_big + n_small);
-    }
+    // the all-pairs flavour streams the caller's frames range by range: any stride that keeps the frames 16-byte aligned
+    const bool use_ap = hp.ap.on && frame_stride_floats % 4 == 0 && (reinterpret_cast<uintptr_t>(coords_dev) & 15) == 0 &&
+                        frame_stride_floats >= 3ll * hp.desc.n_atoms;
+    Chunking ck;
+    if (!make_chunks(n_frames, use_ap ? hp.ap.frames_per_stage : hp.frames_per_stage, use_ap ? hp.ap.max_chunks : hp.max_chunks,
+                     use_ap ? (int64_t)hp.ap.tiles.size() : (int64_t)hp.tiles.size(), use_ap ? hp.ap.n_ctas : hp.n_ctas, ck))
+        return fail(CV_E_INVALID, "too many frames for one run: split the call");
+    rp.chunk_frames = ck.chunk_frames; rp.tail_frames = ck.tail_frames; rp.n_big_chunks = ck.n_big_chunks; rp.n_chunks = ck.n_chunks;
     rp.queue = reinterpret_cast<unsigned int*>(workspace_dev);
     // Lean run (a contact map: flags / scores / occupancy, no feature matrix, no moments): the kernel flavour that
     // skips the moment accumulation and, without a box, the IEEE square root (flag decided on the squared distance).
@@ -415,10 +516,32 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
     }
     rp.pair_thr = hp.pair_thr; rp.pair_thr2 = hp.pair_thr2; rp.hb_dthr = hp.hb_dthr; rp.hb_athr = hp.hb_athr;
 
-    CV_CUDA(cudaMemsetAsync(rp.queue, 0, sizeof(unsigned int), st));
+    CV_CUDA(cudaMemsetAsync(rp.queue, 0, 128, st));       // work counters (the all-pairs flavour keeps two, 64 bytes apart)
     if (rp.score) CV_CUDA(cudaMemsetAsync(rp.score, 0, sizeof(int32_t) * n_frames, st));
 
     cudaError_t e;
+    if (use_ap) {
+        ApParams ap{};
+        ap.coords = coords_dev; ap.frame_stride = frame_stride_floats; ap.n_frames = n_frames;
+        ap.tiles = plan->d_ap_tiles; ap.row_of_word = plan->d_ap_row_of_word; ap.row_off = plan->d_ap_row_off;
+        ap.n_tiles = (int)hp.ap.tiles.size(); ap.minsep = hp.ap.minsep;
+        ap.frames_per_stage = hp.ap.frames_per_stage; ap.n_stages = hp.ap.n_stages; ap.stage_floats = hp.ap.stage_floats;
+        ap.chunk_frames = ck.chunk_frames; ap.tail_frames = ck.tail_frames; ap.n_big_chunks = ck.n_big_chunks; ap.n_chunks = ck.n_chunks;
+        ap.queue = rp.queue; ap.dist = rp.dist; ap.flags = rp.flags; ap.score = rp.score;
+        ap.P = hp.P; ap.W = hp.W;
+        ap.occ_part = rp.occ_part; ap.sum_part = rp.sum_part; ap.sq_part = rp.sq_part;
+        ap.pair_thr = hp.pair_thr; ap.pair_thr2 = hp.pair_thr2;
+        // fast tiles (listed first) with the fast flavour, the rest with the general one; the fast body stores the distance
+        // matrix unconditionally, so a run that wants moments without it takes the general flavour throughout
+        const int n_fast = (lean || rp.dist) ? hp.ap.n_fast_tiles : 0;
+        ApParams gen = ap;
+        gen.tiles = ap.tiles + n_fast; gen.n_tiles = ap.n_tiles - n_fast; gen.queue = ap.queue + 16;
+        ap.n_tiles = n_fast;
+        e = lean ? launch_allpairs<true, true>(plan, ap, st) : launch_allpairs<false, true>(plan, ap, st);
+        if (e == cudaSuccess) e = lean ? launch_allpairs<true, false>(plan, gen, st) : launch_allpairs<false, false>(plan, gen, st);
+        if (e != cudaSuccess) return fail(CV_E_CUDA, std::string("allpairs_kernel launch: ") + cudaGetErrorString(e));
+        g_launches += (n_fast > 0 && gen.n_tiles > 0) ? 1 : 0;
+    } else {
     // TMA ring (plan-order blocks or whole small frames) unless the plan gathers from the caller's frames
     const bool pipe = hp.mode != CV_MODE_DIRECT;
 #define CV_LAUNCH(B, P_) (lean ? launch_features<B, P_, true>(plan, rp, st) : launch_features<B, P_, false>(plan, rp, st))
@@ -433,6 +556,7 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
     }
 #undef CV_LAUNCH
     if (e != cudaSuccess) return fail(CV_E_CUDA, std::string("features_kernel launch: ") + cudaGetErrorString(e));
+    }
     g_launches += 1;
     if (want_agg) {
         const unsigned blocks = (unsigned)((F + 31) / 32);

@@ -74,6 +74,53 @@ struct RunParams {
     int32_t whole_frame;        // 1: a stage is frames_per_stage consecutive whole frames (one bulk copy)
 };
 
+// ------------------------------------------------------------------------------------------------
+// All-pairs path (cv_allpairs.cuh): the i-major list of CAVIAR-1.0.py:331 / :667 without a box
+// ------------------------------------------------------------------------------------------------
+// The list is cut into WINDOWS of 128 consecutive pairs (= 4 flag words, window b covers pairs [128 b, 128 b + 128)).
+// A warp owns TWO windows for a whole work item (8 pairs per lane: lane l evaluates pairs 128 b + 32 m + l, m < 4, of
+// both), a tile is 7 warps = 14 windows.  Windows that lie inside one row of the pair matrix ("fast": atom i is
+// warp-uniform, atom j is affine in the slot) are grouped 2-D -- 14 consecutive rows of the same 128-column band --
+// so that a tile needs ~270 atoms of the frame instead of all of them; windows that contain a row boundary ("general":
+// every lane keeps its own (i, j) per slot) are grouped by row.  A tile's atoms are one or two contiguous ranges of
+// the frame, streamed by TMA as they are.
+constexpr int kApSlots  = 4;                       // flag words per window
+constexpr int kApWindow = 32 * kApSlots;           // pairs per window
+constexpr int kApWarps  = kConsumerThreads / 32;   // windows pairs per tile: one per consumer warp
+constexpr int kApMinGap = 32;                      // atoms: a hole at least this wide splits a tile's atoms into two ranges
+
+struct ApTile {
+    int32_t blk[2][kApWarps];   // window index of warp w (first / second window), -1 = none
+    int32_t fast_mask;          // bit w: both windows of warp w are whole single-row windows
+    int32_t a0, n0;             // atoms [a0, a0 + n0) of the frame (multiples of 4) ...
+    int32_t a1, n1;             // ... and [a1, a1 + n1), n1 = 0: one range
+    int32_t reserved;
+};
+
+struct ApParams {
+    const float* coords;        // the caller's frames, AoS xyz
+    long long    frame_stride;  // floats between frames (multiple of 4)
+    long long    n_frames;
+    const ApTile*  tiles;
+    const int32_t* row_of_word; // [ceil(P/32)]: row (atom i) of pair 32 w
+    const int32_t* row_off;     // [n_rows + 1]: first pair of row i; row_off[n_rows] = P
+    int32_t n_tiles;
+    int32_t minsep;             // j >= i + minsep
+    int32_t frames_per_stage;
+    int32_t n_stages;
+    int32_t stage_floats;       // floats reserved per pipeline stage
+    int32_t chunk_frames, tail_frames, n_big_chunks, n_chunks;     // work queue, as in RunParams
+    unsigned int* queue;
+    float*    dist;
+    uint32_t* flags;
+    int32_t*  score;
+    long long P, W;
+    unsigned long long* occ_part;
+    double* sum_part;
+    double* sq_part;
+    float pair_thr, pair_thr2;
+};
+
 constexpr int kQueueBytes = 256;        // the work counter lives at the head of the caller's workspace
 constexpr int kMinChunkFrames = 32;     // ... but never fewer frames per item than this (short blocks of the host path)
 constexpr int kMinTailFrames = 8;       // ... except the quarter-size items of the tail (per-item flush = 24 B per feature)

@@ -20,6 +20,17 @@
 
 namespace cv {
 
+// The all-pairs flavour (cv_allpairs.cuh) of a plan whose pair list is the reference's own i-major list.
+struct ApHost {
+    bool on = false;
+    int minsep = 0, n_rows = 0;
+    std::vector<int32_t> row_off;       // [n_rows + 1] first pair of row i
+    std::vector<int32_t> row_of_word;   // [ceil(P / 32)] row of pair 32 w
+    std::vector<ApTile> tiles;          // fast tiles first, general tiles last (the queue hands the last ones out first)
+    int n_fast_windows = 0, n_windows = 0, n_fast_tiles = 0;
+    int frames_per_stage = 0, n_stages = 0, stage_floats = 0, smem_bytes = 0, occupancy = 2, n_ctas = 0, max_chunks = 1;
+};
+
 struct HostPlan {
     CvPlanDesc desc{};
     std::vector<int32_t> pairs, triplets;
@@ -38,6 +49,7 @@ struct HostPlan {
     int max_chunks = 1;                // upper bound of frame chunks per run (sizes the workspace)
     int64_t P = 0, A = 0, W = 0, Wp = 0;
     float pair_thr = 0.f, pair_thr2 = 0.f, hb_dthr = 0.f, hb_athr = 0.f;
+    ApHost ap;
 };
 
 inline float f32_at_or_above(double c) {     // smallest float t with (double)t >= c:  (double)d < c  <=>  d < t
@@ -136,6 +148,8 @@ inline int64_t assign_bank_slots(const HostPlan& hp, const TileDesc& t, const st
     }
     return collisions;
 }
+
+inline void build_allpairs(HostPlan& hp);
 
 // Returns "" on success, otherwise the reason.
 inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
@@ -327,7 +341,177 @@ inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
     // kItemsPerCta items, which bounds the tail imbalance without inflating the partial-aggregate buffers.
     hp.n_ctas = d.n_ctas > 0 ? d.n_ctas : hp.n_sms * hp.occupancy;
     hp.max_chunks = std::max(1, (kItemsPerCta * hp.n_ctas + C - 1) / C);
+    build_allpairs(hp);
+    if (hp.ap.on) hp.max_chunks = std::max(hp.max_chunks, hp.ap.max_chunks);     // the workspace serves either kernel
     return "";
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// All-pairs plans
+// ------------------------------------------------------------------------------------------------
+// Is the pair list exactly [(i, j) for i in range(n) for j in range(i + minsep, n)] (CAVIAR-1.0.py:331)?
+inline bool is_all_pairs(const HostPlan& hp, int& minsep) {
+    const int64_t n = hp.desc.n_atoms, P = hp.P;
+    if (P < 1 || hp.pairs[0] != 0) return false;
+    const int64_t m = hp.pairs[1];
+    if (m < 1 || m >= n) return false;
+    const int64_t rows = n - m;
+    if (P != rows * (rows + 1) / 2) return false;
+    int64_t k = 0;
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = i + m; j < n; ++j, ++k)
+            if (hp.pairs[2 * k] != i || hp.pairs[2 * k + 1] != j) return false;
+    minsep = (int)m;
+    return true;
+}
+
+// Cuts an all-pairs list into windows and 2-D tiles (cv_common.h).  Leaves hp.ap.on false when the list is not an
+// all-pairs list, when the frames cannot be streamed by TMA as they are (n_atoms % 4), or when too few windows lie
+// inside a single row for the geometry to pay (short rows: small selections stay on the generic kernel).
+inline void build_allpairs(HostPlan& hp) {
+    ApHost& ap = hp.ap;
+    ap = ApHost();
+    const CvPlanDesc& d = hp.desc;
+    if (d.box_kind != CV_BOX_NONE || hp.A != 0 || (d.flags & (CV_PLAN_FORCE_DIRECT | CV_PLAN_FORCE_STAGED))) return;
+    if (d.n_atoms % 4 != 0 || hp.P >= (1ll << 30) || hp.mode == CV_MODE_STAGED) return;   // (4 P bytes per row in 32 bits; staged plans take plan-order frames)
+    if (const char* e = std::getenv("CAVIAR_NO_ALLPAIRS")) if (atoi(e) != 0) return;
+    int minsep = 0;
+    if (!is_all_pairs(hp, minsep)) return;
+    const int n = d.n_atoms;
+    const int64_t P = hp.P;
+    ap.minsep = minsep;
+    ap.n_rows = n - minsep;
+    ap.row_off.resize((size_t)ap.n_rows + 1);
+    {
+        int64_t o = 0;
+        for (int i = 0; i < ap.n_rows; ++i) { ap.row_off[i] = (int32_t)o; o += n - minsep - i; }
+        ap.row_off[ap.n_rows] = (int32_t)o;
+    }
+    ap.row_of_word.resize((size_t)hp.Wp);
+    for (int64_t w = 0, r = 0; w < hp.Wp; ++w) {
+        while (32 * w >= ap.row_off[r + 1]) ++r;
+        ap.row_of_word[w] = (int32_t)r;
+    }
+    auto row_of = [&](int64_t k) { int r = ap.row_of_word[k >> 5]; while (k >= ap.row_off[r + 1]) ++r; return r; };
+
+    // windows: fast = whole and inside one row
+    const int nb = (int)((P + kApWindow - 1) / kApWindow);
+    ap.n_windows = nb;
+    struct Fast { int band, row, b; };
+    std::vector<Fast> fast;
+    std::vector<int> gen;
+    for (int b = 0; b < nb; ++b) {
+        const int64_t k0 = (int64_t)b * kApWindow, k1 = std::min<int64_t>(P, k0 + kApWindow) - 1;
+        const int i0 = row_of(k0), i1 = row_of(k1);
+        if (i0 == i1 && k0 + kApWindow <= P) {
+            const int j0 = i0 + minsep + (int)(k0 - ap.row_off[i0]);
+            fast.push_back({j0 / kApWindow, i0, b});
+        } else {
+            gen.push_back(b);
+        }
+    }
+    std::sort(fast.begin(), fast.end(), [](const Fast& x, const Fast& y) { return x.band != y.band ? x.band < y.band : (x.row != y.row ? x.row < y.row : x.b < y.b); });
+    // pairs of windows -> warps, 7 warps -> tile; fast tiles never straddle two bands; an odd window of a band joins the general ones
+    struct Warp { int b0, b1; bool fast; };
+    std::vector<std::vector<Warp>> tiles;
+    {
+        size_t q = 0;
+        while (q < fast.size()) {
+            size_t e = q;
+            while (e < fast.size() && fast[e].band == fast[q].band) ++e;
+            std::vector<Warp> cur;
+            int first_row = 0;
+            for (; q + 1 < e; q += 2) {
+                // (the last band only holds the rows whose alignment puts a whole window at its very start: a tile there
+                // would otherwise span hundreds of rows, i.e. hundreds of atoms i)
+                if (!cur.empty() && fast[q + 1].row - first_row > 96) { tiles.push_back(cur); cur.clear(); }
+                if (cur.empty()) first_row = fast[q].row;
+                cur.push_back({fast[q].b, fast[q + 1].b, true});
+                if ((int)cur.size() == kApWarps) { tiles.push_back(cur); cur.clear(); }
+            }
+            if (q < e) { gen.push_back(fast[q].b); ++q; }
+            if (!cur.empty()) tiles.push_back(cur);
+        }
+        ap.n_fast_windows = 0;
+        ap.n_fast_tiles = (int)tiles.size();
+        for (const auto& t : tiles) ap.n_fast_windows += 2 * (int)t.size();
+        std::sort(gen.begin(), gen.end());
+        std::vector<Warp> cur;
+        for (size_t g = 0; g < gen.size(); g += 2) {
+            cur.push_back({gen[g], g + 1 < gen.size() ? gen[g + 1] : -1, false});
+            if ((int)cur.size() == kApWarps) { tiles.push_back(cur); cur.clear(); }
+        }
+        if (!cur.empty()) tiles.push_back(cur);
+    }
+    // not worth it when most windows cross rows (rows shorter than ~3 windows), or when there is too little work to tile
+    if (10 * (int64_t)ap.n_fast_windows < 6 * (int64_t)nb) return;
+
+    // atoms of every tile: one or two contiguous ranges of the frame
+    std::vector<uint8_t> need((size_t)n);
+    int max_atoms = 0;
+    ap.tiles.resize(tiles.size());
+    for (size_t c = 0; c < tiles.size(); ++c) {
+        ApTile& t = ap.tiles[c];
+        for (int w = 0; w < kApWarps; ++w) t.blk[0][w] = t.blk[1][w] = -1;
+        t.fast_mask = 0; t.reserved = 0;
+        std::fill(need.begin(), need.end(), 0);
+        for (size_t w = 0; w < tiles[c].size(); ++w) {
+            const Warp& wp = tiles[c][w];
+            t.blk[0][w] = wp.b0; t.blk[1][w] = wp.b1;
+            if (wp.fast) t.fast_mask |= 1 << w;
+            for (int b : {wp.b0, wp.b1}) {
+                if (b < 0) continue;
+                int64_t k = (int64_t)b * kApWindow;
+                const int64_t k1 = std::min<int64_t>(P, k + kApWindow);
+                while (k < k1) {                                   // row by row
+                    const int i = row_of(k);
+                    const int64_t ke = std::min<int64_t>(k1, ap.row_off[i + 1]);
+                    need[i] = 1;
+                    const int j0 = i + minsep + (int)(k - ap.row_off[i]);
+                    std::fill(need.begin() + j0, need.begin() + j0 + (ke - k), 1);
+                    k = ke;
+                }
+            }
+        }
+        int lo = 0, hi = n - 1;
+        while (!need[lo]) ++lo;
+        while (!need[hi]) --hi;
+        int gap_lo = -1, gap_len = 0;                              // widest hole inside [lo, hi]
+        for (int a = lo; a <= hi;) {
+            if (need[a]) { ++a; continue; }
+            int e = a;
+            while (!need[e]) ++e;
+            if (e - a > gap_len) { gap_len = e - a; gap_lo = a; }
+            a = e;
+        }
+        t.a0 = lo / 4 * 4;
+        t.a1 = 0; t.n1 = 0;
+        if (gap_len >= kApMinGap) {
+            const int end0 = round_up(gap_lo, 4), beg1 = (gap_lo + gap_len) / 4 * 4;
+            if (beg1 > end0) {
+                t.n0 = end0 - t.a0;
+                t.a1 = beg1; t.n1 = round_up(hi + 1, 4) - beg1;
+            }
+        }
+        if (t.n1 == 0) t.n0 = round_up(hi + 1, 4) - t.a0;
+        max_atoms = std::max(max_atoms, t.n0 + t.n1);
+    }
+
+    // ring geometry: 8 frames per stage, 3 stages, 2 CTAs per SM
+    const int bar_bytes = 2 * kMaxStages * 8 + kMaxStages * 24;
+    const int frame_b = 12 * max_atoms;
+    int fb = 8, ns = 3;
+    if (const char* e = std::getenv("CAVIAR_AP_FB")) fb = std::max(1, std::min(32, atoi(e)));
+    if (const char* e = std::getenv("CAVIAR_AP_STAGES")) ns = std::max(2, std::min(kMaxStages, atoi(e)));
+    while (fb > 1 && ns * fb * frame_b + bar_bytes > 110 * 1024) fb /= 2;
+    if (ns * fb * frame_b + bar_bytes > 110 * 1024) return;
+    ap.frames_per_stage = fb; ap.n_stages = ns; ap.stage_floats = fb * 3 * max_atoms;
+    ap.smem_bytes = ns * fb * frame_b + bar_bytes;
+    ap.occupancy = 2;
+    ap.n_ctas = d.n_ctas > 0 ? d.n_ctas : hp.n_sms * ap.occupancy;
+    ap.max_chunks = std::max(1, (kItemsPerCta * ap.n_ctas + (int)ap.tiles.size() - 1) / (int)ap.tiles.size());
+    ap.on = true;
 }
 
 inline void fill_info(const HostPlan& hp, CvPlanInfo& info) {
@@ -349,6 +533,15 @@ inline void fill_info(const HostPlan& hp, CvPlanInfo& info) {
     info.gather_bank_conflicts = hp.bank_conflict_refs;
     info.staged_fixedpoint_floats = 0;       // (ABI 2 field) the staged layout is raw float32 throughout
     info.algorithmic_bytes_per_frame = 12 * hp.n_distinct + box_b + 4 * hp.P + 4 * hp.A + 4 * hp.W + 4;
+    if (hp.ap.on) {
+        info.mode = CV_MODE_ALLPAIRS;
+        info.n_tiles = (int)hp.ap.tiles.size();
+        info.n_ctas = hp.ap.n_ctas;
+        info.threads_per_cta = kConsumerThreads + kProducerThreads;
+        info.stages = hp.ap.n_stages;
+        info.frames_per_stage = hp.ap.frames_per_stage;
+        info.smem_bytes = hp.ap.smem_bytes;
+    }
 }
 
 }  // namespace cv

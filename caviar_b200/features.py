@@ -149,6 +149,17 @@ class FeaturePlan:
         self.mode = int(info.mode)
         self.device = device
 
+    def allpairs_check(self) -> dict:
+        """Host-side verification of the all-pairs geometry (``mode_name == "allpairs"``): the C side runs the kernel's
+        own per-thread set-up for every tile, warp and lane and checks that every pair is evaluated exactly once from
+        the right atoms.  Raises on a violation; returns the geometry statistics (``n_tiles`` = 0: flavour not used)."""
+        stats = np.zeros(8, dtype=np.int64)
+        got = _lib.lib.caviar_plan_allpairs_check(C.byref(self._desc), int(self._sms), stats.ctypes.data)
+        if got < 0:
+            check(int(got))
+        keys = ("windows", "fast_windows", "max_tile_atoms", "frames_per_stage", "stages", "smem_bytes", "mean_tile_atoms", "n_ctas")
+        return {"n_tiles": int(got), **{k: int(v) for k, v in zip(keys, stats)}}
+
     def layout(self) -> dict:
         """The planner's tables (host-side, no CUDA): ``tiles`` (n_tiles, 8) = kind, f_begin, n_feat, idx_off, grp_off,
         grp_floats, 0, 0; ``idx`` (3, n_tiles*896) float offsets inside a tile's block; ``src_off`` (S,)."""

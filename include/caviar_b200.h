@@ -74,6 +74,9 @@ extern "C" {
 #define CV_MODE_DIRECT    0    /* gather from global memory, any frame stride */
 #define CV_MODE_ZEROCOPY  1    /* TMA-stream the caller's frames as they are (small, aligned frames) */
 #define CV_MODE_STAGED    2    /* frames in plan order (per-tile blocks of raw float32 xyz), TMA-streamed */
+#define CV_MODE_ALLPAIRS  3    /* the reference's own list -- all (i, j >= i + minsep), i-major (CAVIAR-1.0.py:331) -- without
+                                  a box: 2-D tiles of the pair matrix, each streaming only its rows' and columns' atoms
+                                  of the caller's frames (n_atoms % 4 == 0, stride a multiple of 4 floats) */
 
 /* atom order of the frames handed to caviar_features_host */
 #define CV_ORDER_CALLER   0    /* (T, n_atoms, 3) as the pair / triplet lists index it */
@@ -151,6 +154,12 @@ int caviar_plan_describe(const CvPlanDesc* desc, int32_t n_sms, CvPlanInfo* info
  *   src_off   [staged_floats_per_frame] int32: staged float j <- float src_off[j] of the input frame
  * Any buffer may be NULL. */
 int caviar_plan_layout(const CvPlanDesc* desc, int32_t n_sms, int32_t* tile_desc, int32_t* idx, int32_t* src_off);
+
+/* Host-side check of the all-pairs geometry (CV_MODE_ALLPAIRS), no CUDA call: runs the kernel's own per-thread set-up for
+ * every tile, warp and lane and verifies that every pair is evaluated exactly once from the right atoms.  Returns the
+ * number of tiles (0: the plan does not use that flavour), < 0 on a violation.  stats (optional, 8 values): windows, fast
+ * windows, largest tile block in atoms, frames per stage, stages, shared-memory bytes, mean atoms per tile, CTAs. */
+int64_t caviar_plan_allpairs_check(const CvPlanDesc* desc, int32_t n_sms, int64_t* stats);
 
 int  caviar_plan_create(const CvPlanDesc* desc, CvPlan** plan);
 void caviar_plan_destroy(CvPlan* plan);

@@ -45,7 +45,7 @@ def test_reference_error_behaviour_needs_no_gpu(cb):
         cb.compute_distances_parallel(x, [(0, 4)])
 
 
-@pytest.mark.parametrize("cfg_id,mode", [(1, "staged"), (2, "staged"), (3, "staged"), (4, "zerocopy")])
+@pytest.mark.parametrize("cfg_id,mode", [(1, "staged"), (2, "staged"), (3, "staged"), (4, "allpairs")])
 def test_plan_describe_configs(cb, cfg_id, mode):
     from caviar_b200 import synthetic as syn
     top = syn.make_topology(cfg_id)

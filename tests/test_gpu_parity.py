@@ -197,7 +197,7 @@ def test_cfg3_triclinic(cb, force, T, compact):
 
 def test_cfg4_all_pairs_contact_map(cb):
     top, x, box, pairs, triplets, res, info = _run_cfg(cb, 4, 24, None)
-    assert info["mode_name"] == "zerocopy" and len(pairs) == 495510
+    assert info["mode_name"] == "allpairs" and len(pairs) == 495510
     _check_features(cb, res, x, box, pairs, triplets, CUTS, exact_dist=True)
 
 
