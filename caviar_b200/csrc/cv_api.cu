@@ -217,6 +217,10 @@ extern "C" int64_t caviar_plan_allpairs_check(const CvPlanDesc* desc, int32_t n_
         auto atom_of = [&](int off) { const int a = off / 3; return a < t.n0 ? t.a0 + a : t.a1 + (a - t.n0); };
         for (int w = 0; w < kApWarps; ++w) {
             const bool fast = (t.fast_mask >> w) & 1;
+            // the fast kernel runs tiles [0, n_fast_tiles): there a warp has two whole windows or none at all
+            if ((int)c < ap.n_fast_tiles && !(fast ? (t.blk[0][w] >= 0 && t.blk[1][w] >= 0) : (t.blk[0][w] < 0 && t.blk[1][w] < 0)))
+                return fail(CV_E_INVALID, "fast tile with a half-filled or general warp" + at);
+            if ((int)c >= ap.n_fast_tiles && fast) return fail(CV_E_INVALID, "general tile with a fast warp" + at);
             int i_uniform[2] = {-1, -1};
             for (int lane = 0; lane < 32; ++lane) {
                 ApThread th;
@@ -499,15 +503,32 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
     const bool use_ap = hp.ap.on && frame_stride_floats % 4 == 0 && (reinterpret_cast<uintptr_t>(coords_dev) & 15) == 0 &&
                         frame_stride_floats >= 3ll * hp.desc.n_atoms;
     Chunking ck;
-    if (!make_chunks(n_frames, use_ap ? hp.ap.frames_per_stage : hp.frames_per_stage, use_ap ? hp.ap.max_chunks : hp.max_chunks,
-                     use_ap ? (int64_t)hp.ap.tiles.size() : (int64_t)hp.tiles.size(), use_ap ? hp.ap.n_ctas : hp.n_ctas, ck))
+    if (use_ap) {
+        // The all-pairs flavour adds its aggregates in place, in chunk order (ApParams::seq): no partial rows, so chunks can
+        // be SHORT -- and that is what a run that emits the distance matrix wants.  The queue is chunk-major, so short items
+        // keep all CTAs within a few hundred frames of each other and the 2 MB rows of the matrix are completed in the L2
+        // within microseconds; with ~1 500-frame items the CTAs drift thousands of rows apart, every 512-byte piece reaches
+        // HBM on its own and the write rate collapses (config 4, 50 000 frames: 5.3e11 -> 6.3e11 evals/s from 1 470- to
+        // 96-frame items; a fill kernel writes 7.5 TB/s on this box, this pattern 3).  Contact-map runs write 1/32 of that
+        // and prefer longer items (fewer pipeline restarts).
+        const bool emits = out && out->dist;
+        int64_t cf = emits ? 96 : 512;
+        if (const char* e = std::getenv("CAVIAR_AP_CHUNK")) cf = std::max(1, atoi(e));
+        const int64_t fb = hp.ap.frames_per_stage, nt = (int64_t)hp.ap.tiles.size();
+        cf = std::max(fb, (cf + fb - 1) / fb * fb);
+        while (cf > 4 * fb && nt * ((n_frames + cf - 1) / cf) < 8ll * hp.ap.n_ctas) cf = std::max(4 * fb, cf / 2 / fb * fb);   // short runs: enough items to balance
+        const int64_t nc = (n_frames + cf - 1) / cf;
+        if (nc >= (1ll << 31) / std::max<int64_t>(nt, 1)) return fail(CV_E_INVALID, "too many frames for one run: split the call");
+        ck.chunk_frames = (int32_t)cf; ck.tail_frames = (int32_t)cf; ck.n_big_chunks = (int32_t)nc; ck.n_chunks = (int32_t)nc;
+    } else if (!make_chunks(n_frames, hp.frames_per_stage, hp.max_chunks, (int64_t)hp.tiles.size(), hp.n_ctas, ck)) {
         return fail(CV_E_INVALID, "too many frames for one run: split the call");
+    }
     rp.chunk_frames = ck.chunk_frames; rp.tail_frames = ck.tail_frames; rp.n_big_chunks = ck.n_big_chunks; rp.n_chunks = ck.n_chunks;
     rp.queue = reinterpret_cast<unsigned int*>(workspace_dev);
     // Lean run (a contact map: flags / scores / occupancy, no feature matrix, no moments): the kernel flavour that
     // skips the moment accumulation and, without a box, the IEEE square root (flag decided on the squared distance).
     const bool lean = !rp.dist && !rp.angle && !want_moments;
-    if (want_agg) {
+    if (want_agg && !use_ap) {
         rp.occ_part = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace_dev) + kQueueBytes);
         if (want_moments) {
             rp.sum_part = reinterpret_cast<double*>(rp.occ_part + (long long)rp.n_chunks * F);
@@ -529,13 +550,18 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
         ap.chunk_frames = ck.chunk_frames; ap.tail_frames = ck.tail_frames; ap.n_big_chunks = ck.n_big_chunks; ap.n_chunks = ck.n_chunks;
         ap.queue = rp.queue; ap.dist = rp.dist; ap.flags = rp.flags; ap.score = rp.score;
         ap.P = hp.P; ap.W = hp.W;
-        ap.occ_part = rp.occ_part; ap.sum_part = rp.sum_part; ap.sq_part = rp.sq_part;
+        ap.seq = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(workspace_dev) + kQueueBytes);
+        CV_CUDA(cudaMemsetAsync(ap.seq, 0, sizeof(unsigned int) * (size_t)ap.n_tiles, st));
+        if (want_agg) {
+            ap.occ = reinterpret_cast<unsigned long long*>(agg->occupancy); ap.occ_f64 = agg->occupancy_f64;
+            ap.sum = agg->sum; ap.sq = agg->sumsq;
+        }
         ap.pair_thr = hp.pair_thr; ap.pair_thr2 = hp.pair_thr2;
         // fast tiles (listed first) with the fast flavour, the rest with the general one; the fast body stores the distance
         // matrix unconditionally, so a run that wants moments without it takes the general flavour throughout
         const int n_fast = (lean || rp.dist) ? hp.ap.n_fast_tiles : 0;
         ApParams gen = ap;
-        gen.tiles = ap.tiles + n_fast; gen.n_tiles = ap.n_tiles - n_fast; gen.queue = ap.queue + 16;
+        gen.tiles = ap.tiles + n_fast; gen.n_tiles = ap.n_tiles - n_fast; gen.queue = ap.queue + 16; gen.seq = ap.seq + n_fast;
         ap.n_tiles = n_fast;
         e = lean ? launch_allpairs<true, true>(plan, ap, st) : launch_allpairs<false, true>(plan, ap, st);
         if (e == cudaSuccess) e = lean ? launch_allpairs<true, false>(plan, gen, st) : launch_allpairs<false, false>(plan, gen, st);
@@ -558,7 +584,7 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
     if (e != cudaSuccess) return fail(CV_E_CUDA, std::string("features_kernel launch: ") + cudaGetErrorString(e));
     }
     g_launches += 1;
-    if (want_agg) {
+    if (want_agg && !use_ap) {
         const unsigned blocks = (unsigned)((F + 31) / 32);
         unsigned long long* occ_out = reinterpret_cast<unsigned long long*>(agg->occupancy);
         const bool many = rp.n_chunks >= kFinalizeManyRows;      // (a function of the run's shape only: reproducible)

@@ -115,9 +115,14 @@ struct ApParams {
     uint32_t* flags;
     int32_t*  score;
     long long P, W;
-    unsigned long long* occ_part;
-    double* sum_part;
-    double* sq_part;
+    // Aggregates are accumulated IN PLACE, in chunk order: item (chunk c, tile) adds its registers to the totals after item
+    // (c - 1, tile) has (seq[tile] == c; the queue is chunk-major, so that item was handed out earlier).  A fixed order,
+    // hence bit-reproducible sums, without per-chunk partial rows -- which lets chunks be short (see caviar_run).
+    unsigned int* seq;              // [n_tiles] zeroed before the launch
+    unsigned long long* occ;        // [P] or nullptr
+    double* occ_f64;                // [P] or nullptr (occupancy as float64, see CvAggregates)
+    double* sum;                    // [P] or nullptr
+    double* sq;
     float pair_thr, pair_thr2;
 };
 

@@ -28,7 +28,7 @@ struct ApHost {
     std::vector<int32_t> row_of_word;   // [ceil(P / 32)] row of pair 32 w
     std::vector<ApTile> tiles;          // fast tiles first, general tiles last (the queue hands the last ones out first)
     int n_fast_windows = 0, n_windows = 0, n_fast_tiles = 0;
-    int frames_per_stage = 0, n_stages = 0, stage_floats = 0, smem_bytes = 0, occupancy = 2, n_ctas = 0, max_chunks = 1;
+    int frames_per_stage = 0, n_stages = 0, stage_floats = 0, smem_bytes = 0, occupancy = 2, n_ctas = 0;
 };
 
 struct HostPlan {
@@ -342,7 +342,6 @@ inline std::string build_plan(const CvPlanDesc& d, int n_sms, HostPlan& hp) {
     hp.n_ctas = d.n_ctas > 0 ? d.n_ctas : hp.n_sms * hp.occupancy;
     hp.max_chunks = std::max(1, (kItemsPerCta * hp.n_ctas + C - 1) / C);
     build_allpairs(hp);
-    if (hp.ap.on) hp.max_chunks = std::max(hp.max_chunks, hp.ap.max_chunks);     // the workspace serves either kernel
     return "";
 }
 
@@ -510,7 +509,6 @@ inline void build_allpairs(HostPlan& hp) {
     ap.smem_bytes = ns * fb * frame_b + bar_bytes;
     ap.occupancy = 2;
     ap.n_ctas = d.n_ctas > 0 ? d.n_ctas : hp.n_sms * ap.occupancy;
-    ap.max_chunks = std::max(1, (kItemsPerCta * ap.n_ctas + (int)ap.tiles.size() - 1) / (int)ap.tiles.size());
     ap.on = true;
 }
 
