@@ -512,7 +512,7 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
         // 96-frame items; a fill kernel writes 7.5 TB/s on this box, this pattern 3).  Contact-map runs write 1/32 of that
         // and prefer longer items (fewer pipeline restarts).
         const bool emits = out && out->dist;
-        int64_t cf = emits ? 96 : 512;
+        int64_t cf = emits ? 128 : 512;
         if (const char* e = std::getenv("CAVIAR_AP_CHUNK")) cf = std::max(1, atoi(e));
         const int64_t fb = hp.ap.frames_per_stage, nt = (int64_t)hp.ap.tiles.size();
         cf = std::max(fb, (cf + fb - 1) / fb * fb);

@@ -410,26 +410,53 @@ inline void build_allpairs(HostPlan& hp) {
             gen.push_back(b);
         }
     }
-    std::sort(fast.begin(), fast.end(), [](const Fast& x, const Fast& y) { return x.band != y.band ? x.band < y.band : (x.row != y.row ? x.row < y.row : x.b < y.b); });
-    // pairs of windows -> warps, 7 warps -> tile; fast tiles never straddle two bands; an odd window of a band joins the general ones
+    // Windows -> warps (two each) -> tiles (7 warps).  A warp takes the windows of two neighbouring rows in one 128-column
+    // band; a tile is 7 warps from consecutive rows of that band, so that its atoms are 14 rows' i and ~270 j.
+    // Fast tiles never straddle two bands; what is left over joins the general windows.
     struct Warp { int b0, b1; bool fast; };
+    struct FastWarp { int band, row, b0, b1; };
+    std::vector<FastWarp> fw;
+    {
+        // (adjacent windows of one row -- 1 KB pieces of the matrix -- were tried and lost 4 % to the wider column bands:
+        // CAVIAR_AP_PAIRING=h builds that geometry)
+        bool horizontal = false;
+        if (const char* e = std::getenv("CAVIAR_AP_PAIRING")) horizontal = e[0] == 'h';
+        std::vector<Fast> odd;                                   // fast is in list order: row-major, b ascending
+        for (size_t q = 0; q < fast.size();) {
+            if (horizontal && q + 1 < fast.size() && fast[q + 1].row == fast[q].row && fast[q + 1].b == fast[q].b + 1) {
+                fw.push_back({1000 + fast[q].band / 2, fast[q].row, fast[q].b, fast[q + 1].b});
+                q += 2;
+            } else {
+                odd.push_back(fast[q]); ++q;
+            }
+        }
+        std::sort(odd.begin(), odd.end(), [](const Fast& x, const Fast& y) { return x.band != y.band ? x.band < y.band : (x.row != y.row ? x.row < y.row : x.b < y.b); });
+        for (size_t q = 0; q < odd.size();) {
+            if (q + 1 < odd.size() && odd[q + 1].band == odd[q].band && odd[q + 1].row - odd[q].row <= 8) {
+                fw.push_back({odd[q].band, odd[q].row, odd[q].b, odd[q + 1].b});
+                q += 2;
+            } else {
+                gen.push_back(odd[q].b); ++q;
+            }
+        }
+        std::sort(fw.begin(), fw.end(), [](const FastWarp& x, const FastWarp& y) { return x.band != y.band ? x.band < y.band : (x.row != y.row ? x.row < y.row : x.b0 < y.b0); });
+    }
     std::vector<std::vector<Warp>> tiles;
     {
         size_t q = 0;
-        while (q < fast.size()) {
+        while (q < fw.size()) {
             size_t e = q;
-            while (e < fast.size() && fast[e].band == fast[q].band) ++e;
+            while (e < fw.size() && fw[e].band == fw[q].band) ++e;
             std::vector<Warp> cur;
             int first_row = 0;
-            for (; q + 1 < e; q += 2) {
-                // (the last band only holds the rows whose alignment puts a whole window at its very start: a tile there
-                // would otherwise span hundreds of rows, i.e. hundreds of atoms i)
-                if (!cur.empty() && fast[q + 1].row - first_row > 96) { tiles.push_back(cur); cur.clear(); }
-                if (cur.empty()) first_row = fast[q].row;
-                cur.push_back({fast[q].b, fast[q + 1].b, true});
+            for (; q < e; ++q) {
+                // (sparse bands -- the last one only holds the rows whose alignment puts a whole window at its very start --
+                // would otherwise make tiles that span hundreds of rows, i.e. hundreds of atoms i)
+                if (!cur.empty() && fw[q].row - first_row > 96) { tiles.push_back(cur); cur.clear(); }
+                if (cur.empty()) first_row = fw[q].row;
+                cur.push_back({fw[q].b0, fw[q].b1, true});
                 if ((int)cur.size() == kApWarps) { tiles.push_back(cur); cur.clear(); }
             }
-            if (q < e) { gen.push_back(fast[q].b); ++q; }
             if (!cur.empty()) tiles.push_back(cur);
         }
         ap.n_fast_windows = 0;
