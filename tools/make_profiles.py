@@ -23,12 +23,12 @@ TAG = sys.argv[1] if len(sys.argv) > 1 else "r02"
 OUT = os.path.join(ROOT, "gpurun_out")
 PROF = os.path.join(ROOT, "profiles")
 
-# capture file -> (traffic.json key, frames in the capture, file stem, command)
+# capture file -> (traffic.json key, frames in the capture, file stem, command[, launches in the capture])
 CAPTURES = [
     ("prof_features", "cfg3", 16384, "features_kernel_cfg3", "tools/gpu_probe.py 3 16384: cv::features_kernel<2,true,false> on raw plan-order frames"),
     ("prof_stage", "cfg3_k0", 16384, "stage_frames_kernel_cfg3", "tools/gpu_probe.py 3 16384: cv::stage_frames_kernel (caller order -> plan order)"),
-    ("prof_cfg4_full", "cfg4", 2048, "features_kernel_cfg4_full", "tools/gpu_cfg4.py 2048: cv::features_kernel<0,true,false>, dist + flags + scores + occupancy + moments"),
-    ("prof_cfg4_lean", "cfg4_lean", 2048, "features_kernel_cfg4_contact_map", "tools/gpu_cfg4.py 2048: cv::features_kernel<0,true,true>, flags + scores + occupancy"),
+    ("prof_cfg4_full", "cfg4", 2048, "allpairs_kernel_cfg4_full", "tools/gpu_cfg4.py 2048: cv::allpairs_kernel<false,true> (fast tiles) + <false,false> (general tiles), dist + flags + scores + occupancy + moments", 2),
+    ("prof_cfg4_lean", "cfg4_lean", 2048, "allpairs_kernel_cfg4_contact_map", "tools/gpu_cfg4.py 2048: cv::allpairs_kernel<true,true> + <true,false>, flags + scores + occupancy", 2),
     ("prof_cfg5", "cfg5", 4096, "features_kernel_cfg5", "tools/gpu_probe.py 5 4096: cv::features_kernel<1,true,false>"),
     ("prof_cov", "cov_n14000_k4096", 1, "cov_gemm_kernel", "tools/gpu_cov.py 14000 4096: cvcov::cov_gemm_kernel (tcgen05 kind::tf32)"),
 ]
@@ -62,32 +62,46 @@ if os.path.exists(launch_csv):
 # 2. raw metrics + traffic
 scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
 traffic = {}
-for stem, key, frames, name, what in CAPTURES:
+for cap in CAPTURES:
+    stem, key, frames, name, what = cap[:5]
+    n_rows = cap[5] if len(cap) > 5 else 1
     rep = os.path.join(OUT, stem + ".ncu-rep")
     if not os.path.exists(rep):
         print("missing", rep)
         continue
-    raw = sh([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep])
-    open(os.path.join(PROF, f"{TAG}_{name}_ncu_raw.txt"), "w").write(f"# {what}\n# ncu --set full --import-source on --clock-control none, one launch\n" + raw)
-    val = {}
-    for line in raw.splitlines():
-        m = re.match(r"(\S+)\s+(\S+)\s+(\S+)$", line.strip())
-        if m:
-            val[m.group(1)] = (m.group(2), m.group(3))
-    try:
-        rd = float(val["dram__bytes_read.sum"][1]) * scale[val["dram__bytes_read.sum"][0]]
-        wr = float(val["dram__bytes_write.sum"][1]) * scale[val["dram__bytes_write.sum"][0]]
-    except KeyError:
-        print("no dram metrics in", rep)
+    text = f"# {what}\n# ncu --set full --import-source on --clock-control none, {n_rows} launch(es)\n"
+    rd = wr = inst = dur_us = issue_w = dram_w = 0.0
+    ok = True
+    for row in range(n_rows):
+        raw = sh([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep, str(row)])
+        text += raw + ("\n" if row + 1 < n_rows else "")
+        val = {}
+        for line in raw.splitlines():
+            m = re.match(r"(\S+)\s+(\S+)\s+(\S+)$", line.strip())
+            if m:
+                val[m.group(1)] = (m.group(2), m.group(3))
+        try:
+            rd += float(val["dram__bytes_read.sum"][1]) * scale[val["dram__bytes_read.sum"][0]]
+            wr += float(val["dram__bytes_write.sum"][1]) * scale[val["dram__bytes_write.sum"][0]]
+        except KeyError:
+            print("no dram metrics in", rep)
+            ok = False
+            break
+        unit, v = val["gpu__time_duration.sum"]
+        us = float(v) * {"ms": 1e3, "us": 1.0, "ns": 1e-3, "s": 1e6}.get(unit, 1.0)
+        dur_us += us
+        issue_w += us * float(val.get("smsp__issue_active.avg.pct_of_peak_sustained_active", ("", "nan"))[1])
+        dram_w += us * float(val.get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", ("", "nan"))[1])
+        inst += float(val.get("smsp__inst_executed.sum", ("", "0"))[1])
+    open(os.path.join(PROF, f"{TAG}_{name}_ncu_raw.txt"), "w").write(text)
+    if not ok:
         continue
-    dur = val["gpu__time_duration.sum"]
     entry = {"dram_bytes_per_frame": (rd + wr) / frames, "dram_bytes_read": rd, "dram_bytes_write": wr,
-             "frames_in_capture": frames, "kernel_duration_under_ncu": f"{dur[1]} {dur[0]}",
-             "issue_active_pct": float(val.get("smsp__issue_active.avg.pct_of_peak_sustained_active", ("", "nan"))[1]),
-             "dram_throughput_pct_of_peak": float(val.get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", ("", "nan"))[1]),
+             "frames_in_capture": frames, "kernel_duration_under_ncu": f"{dur_us / 1e3:.6f} ms",
+             "issue_active_pct": issue_w / dur_us, "dram_throughput_pct_of_peak": dram_w / dur_us,
              "source": f"profiles/{TAG}_{name}_ncu_raw.txt ({what})"}
-    if "smsp__inst_executed.sum" in val:
-        entry["warp_instructions_per_frame"] = float(val["smsp__inst_executed.sum"][1]) / frames
+    if inst:
+        entry["warp_instructions_per_frame"] = inst / frames
     traffic[key] = entry
     print(key, {k: entry[k] for k in ("dram_bytes_per_frame", "kernel_duration_under_ncu", "issue_active_pct")})
 if traffic:
