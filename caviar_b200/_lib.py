@@ -96,6 +96,9 @@ SYMBOLS = {
                                            C.c_void_p]),
     "caviar_compact_frames_soa_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64,
                                                C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "caviar_xtc_index": (C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int32)]),
+    "caviar_xtc_decode_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_float,
+                                         C.c_void_p, C.c_void_p]),
     "caviar_format_csv": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                       C.c_int32, C.c_void_p, C.c_int64]),
     "caviar_last_error": (C.c_char_p, []),

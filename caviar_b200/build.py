@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libcaviar_b200.so")
-SOURCES = ["cv_api.cu", "cv_cov.cu"]
-HEADERS = ["cv_device.cuh", "cv_plan.hpp", "cv_common.h", os.path.join("..", "..", "include", "caviar_b200.h")]
+SOURCES = ["cv_api.cu", "cv_cov.cu", "cv_xtc.cu"]
+HEADERS = ["cv_device.cuh", "cv_allpairs.cuh", "cv_plan.hpp", "cv_common.h", os.path.join("..", "..", "include", "caviar_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",   # B200 only: no PTX for other targets, no fallback arch

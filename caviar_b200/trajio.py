@@ -21,6 +21,7 @@ when no NetCDF file is at hand.
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 import sys
 from dataclasses import dataclass
@@ -244,6 +245,13 @@ class Trajectory:
         self._dcd = None
         self._trr = None
         self._crd = None
+        self._xtc = None
+        if ext == ".xtc":
+            self._xtc = _XtcFile(path)
+            self._xyz = None
+            self._len = self._ang = None
+            self.n_frames, self.n_atoms = self._xtc.n_frames, self._xtc.n_atoms
+            return
         if ext in (".mdcrd", ".crd", ".trj"):
             if not n_atoms:
                 sys.exit("[ERR] una traiettoria Amber ASCII (mdcrd) non contiene il numero di atomi: serve la topologia")
@@ -277,11 +285,9 @@ class Trajectory:
             if magic[:3] != b"CDF" or magic[3:4] not in (b"\x01", b"\x02"):
                 if magic[:8] == b"\x89HDF\r\n\x1a\n":
                     what = "NetCDF-4 / HDF5 (convert with `cpptraj` or `ncks -3` to NetCDF-3, the Amber convention)"
-                elif ext == ".xtc":
-                    what = "GROMACS XTC (compressed coordinates are not read; convert to .trr, .dcd or .nc)"
                 else:
                     what = f"unknown format '{ext or path}'"
-                sys.exit(f"[ERR] formato di traiettoria non supportato: {what}. Supportati: Amber NetCDF-3 (.nc), mdcrd, DCD, TRR, .npy")
+                sys.exit(f"[ERR] formato di traiettoria non supportato: {what}. Supportati: Amber NetCDF-3 (.nc), mdcrd, DCD, TRR, XTC, .npy")
             from scipy.io import netcdf_file
             self._nc = netcdf_file(path, "r", mmap=True)
             if "coordinates" not in self._nc.variables:
@@ -295,6 +301,8 @@ class Trajectory:
     def has_box(self) -> bool:
         if self._crd is not None:
             return self._crd.has_box
+        if self._xtc is not None:
+            return self.n_frames > 0 and bool(np.all(np.diag(self._xtc.box(0, 1)[0]) > 0))
         if self._trr is not None:
             return self._trr.has_box and self.n_frames > 0 and bool(np.all(np.diag(self._trr.box(0, 1)[0]) > 0))
         if self._dcd is not None:
@@ -308,8 +316,8 @@ class Trajectory:
             return None
         if self._crd is not None:
             return "ortho"                                        # an mdcrd box line holds the three edge lengths only
-        if self._trr is not None:
-            h = self._trr.box(0, 1)[0]
+        if self._trr is not None or self._xtc is not None:
+            h = (self._trr or self._xtc).box(0, 1)[0]
             off = np.abs(h - np.diag(np.diag(h))).max()
             return "ortho" if off <= 1e-6 * np.abs(np.diag(h)).max() else "triclinic"
         ang = self._dcd.cell(0, 1)[1][0] if self._dcd is not None else np.asarray(self._ang[0], dtype=np.float64)
@@ -318,7 +326,7 @@ class Trajectory:
     def coords(self, lo: int, hi: int, stride: int = 1) -> np.ndarray:
         if self._crd is not None:
             return self._crd.coords(lo, hi, stride)
-        if self._dcd is not None or self._trr is not None:
+        if self._dcd is not None or self._trr is not None or self._xtc is not None:
             return self.coords_of(np.arange(self.n_atoms), lo, hi, stride)
         return np.ascontiguousarray(self._xyz[lo:hi:stride], dtype=np.float32)
 
@@ -334,6 +342,10 @@ class Trajectory:
             out = np.empty((n, len(atoms), 3), dtype=np.float32)
         if self._crd is not None:                                  # text: parse the frames, then pick the atoms
             out[...] = self._crd.coords(lo, hi, stride)[:, atoms, :]
+            return out
+        if self._xtc is not None:                                  # decompressed frame by frame on the host threads, in Angstrom
+            if n and len(atoms):
+                self._xtc.read(np.arange(lo, hi, stride), atoms, out)
             return out
         if self._trr is not None:
             if n and len(atoms):
@@ -367,8 +379,8 @@ class Trajectory:
             return None
         if self._crd is not None:
             return self._crd.box(lo, hi, stride)
-        if self._trr is not None:
-            h = self._trr.box(lo, hi, stride) * 10.0                 # nm -> Angstrom; rows = box vectors (a along x)
+        if self._trr is not None or self._xtc is not None:
+            h = (self._trr or self._xtc).box(lo, hi, stride) * 10.0  # nm -> Angstrom; rows = box vectors (a along x)
             return np.stack([h[:, 0, 0], h[:, 1, 1], h[:, 2, 2]], axis=1).astype(np.float32) if kind == "ortho" \
                 else h.astype(np.float32)
         if self._dcd is not None:
@@ -387,6 +399,9 @@ class Trajectory:
         if self._trr is not None:
             self._trr.close()
             self._trr = None
+        if self._xtc is not None:
+            self._xtc.close()
+            self._xtc = None
         if self._dcd is not None:
             self._dcd.close()
             self._dcd = None
@@ -398,6 +413,178 @@ class Trajectory:
                 pass
             self._nc = None
 
+
+
+class _XtcFile:
+    """GROMACS XTC (XDR header + compressed integer coordinates per frame) over a read-only memory map.  The frames are
+    indexed once (they have different sizes) and decompressed by the native library (``cv_xtc.cu``), in parallel, only
+    the selected atoms coming back.  Precision is whatever the writer chose (0.001 nm by default): the positions in the
+    file already ARE rounded, nothing is lost or added here."""
+
+    def __init__(self, path: str):
+        from . import _lib
+        self._mm = np.memmap(path, dtype=np.uint8, mode="r")
+        n_atoms = C.c_int32(0)
+        n = _lib.lib.caviar_xtc_index(self._mm.ctypes.data, self._mm.size, None, 0, C.byref(n_atoms))
+        if n < 0:
+            why = (_lib.lib.caviar_last_error() or b"").decode("utf-8", "replace")
+            sys.exit(f"[ERR] traiettoria XTC non leggibile ({path}): {why}")
+        self.offsets = np.zeros(max(int(n), 1), dtype=np.int64)
+        if n > 0:
+            got = _lib.lib.caviar_xtc_index(self._mm.ctypes.data, self._mm.size, self.offsets.ctypes.data, int(n), C.byref(n_atoms))
+            assert got == n
+        self.n_frames, self.n_atoms = int(n), int(n_atoms.value)
+
+    def read(self, frames: np.ndarray, atoms: np.ndarray, out: np.ndarray) -> None:
+        from . import _lib
+        off = np.ascontiguousarray(self.offsets[np.asarray(frames, dtype=np.int64)])
+        _lib.check(_lib.lib.caviar_xtc_decode_host(self._mm.ctypes.data, self._mm.size, off.ctypes.data, len(off),
+                                                   atoms.ctypes.data, len(atoms), 10.0, out.ctypes.data, None))
+
+    def box(self, lo: int, hi: int, stride: int = 1) -> np.ndarray:
+        """(n, 3, 3) float64, rows = box vectors, in nm (like ``_TrrFile.box``)."""
+        idx = np.arange(lo, hi, max(1, stride))
+        out = np.empty((len(idx), 3, 3), dtype=np.float64)
+        for k, t in enumerate(idx):
+            o = int(self.offsets[t]) + 16
+            out[k] = self._mm[o:o + 36].view(">f4").reshape(3, 3)
+        return out
+
+    def close(self):
+        self._mm = None
+
+
+_XTC_MAGIC = [0] * 9 + [8, 10, 12, 16, 20, 25, 32, 40, 50, 64, 80, 101, 128, 161, 203, 256, 322, 406, 512, 645, 812, 1024, 1290,
+                        1625, 2048, 2580, 3250, 4096, 5060, 6501, 8192, 10321, 13003, 16384, 20642, 26007, 32768, 41285, 52015,
+                        65536, 82570, 104031, 131072, 165140, 208063, 262144, 330280, 416127, 524287, 660561, 832255, 1048576,
+                        1321122, 1664510, 2097152, 2642245, 3329021, 4194304, 5284491, 6658042, 8388607, 10568983, 13316085,
+                        16777216]
+
+
+class _BitWriter:
+    def __init__(self):
+        self.acc, self.n, self.out = 0, 0, bytearray()
+
+    def put(self, nbits: int, value: int):
+        if nbits <= 0:
+            return
+        self.acc = (self.acc << nbits) | (int(value) & ((1 << nbits) - 1))
+        self.n += nbits
+        while self.n >= 8:
+            self.n -= 8
+            self.out.append((self.acc >> self.n) & 0xFF)
+        self.acc &= (1 << self.n) - 1
+
+    def put3(self, nbits: int, sizes, nums):
+        """Three integers as one mixed-radix number, 8-bit groups, least significant group first."""
+        v = (int(nums[0]) * int(sizes[1]) + int(nums[1])) * int(sizes[2]) + int(nums[2])
+        while nbits > 8:
+            self.put(8, v & 0xFF)
+            v >>= 8
+            nbits -= 8
+        self.put(nbits, v)
+
+    def bytes(self) -> bytes:
+        tail = bytes([(self.acc << (8 - self.n)) & 0xFF]) if self.n else b""
+        return bytes(self.out) + tail
+
+
+def write_xtc(path: str, xyz_nm: np.ndarray, box_nm=None, precision: float = 1000.0, magic: int = 1995) -> np.ndarray:
+    """Test / tooling writer: ``xyz_nm`` (T, N, 3) in nm, compressed the way GROMACS' xdrfile does it -- integers
+    ``round(x * precision)``, one mixed-radix number per atom over the frame's bounding box, runs of atoms close to their
+    predecessor as small offsets in the adaptive radix, the first two atoms of a run swapped -- or, for N <= 9, as plain
+    floats.  Returns the positions a reader must reproduce (T, N, 3) in nm (= the rounded integers / precision)."""
+    import struct
+    xyz_nm = np.asarray(xyz_nm, dtype=np.float32)
+    T, N = xyz_nm.shape[:2]
+    want = np.empty_like(xyz_nm)
+    first, last = 9, len(_XTC_MAGIC)
+    with open(path, "wb") as fh:
+        for t in range(T):
+            box = np.zeros((3, 3), np.float32) if box_nm is None else np.asarray(box_nm, np.float32).reshape(-1, 3, 3)[min(t, len(np.asarray(box_nm).reshape(-1, 3, 3)) - 1)]
+            fh.write(struct.pack(">iiif", magic, N, t, float(t)) + box.astype(">f4").tobytes() + struct.pack(">i", N))
+            if N <= 9:
+                fh.write(xyz_nm[t].astype(">f4").tobytes())
+                want[t] = xyz_nm[t]
+                continue
+            ints = np.rint(xyz_nm[t].astype(np.float64) * precision).astype(np.int64)
+            want[t] = (ints.astype(np.float32) * np.float32(1.0 / np.float32(precision)))
+            lo, hi = ints.min(axis=0), ints.max(axis=0)
+            size = (hi - lo + 1).astype(np.int64)
+            if int(size.max()) > 0xFFFFFF:
+                bits3, bitsize = [int(v).bit_length() for v in size], 0
+            else:
+                bits3, bitsize = None, int(int(size[0]) * int(size[1]) * int(size[2])).bit_length()
+            diffs = np.abs(np.diff(ints, axis=0)).sum(axis=1)
+            mindiff = int(diffs.min()) if len(diffs) else 0
+            smallidx = first
+            while smallidx < last - 1 and _XTC_MAGIC[smallidx] < mindiff:
+                smallidx += 1
+            maxidx = min(last - 1, smallidx + 8)
+            minidx = maxidx - 8
+            smaller = _XTC_MAGIC[max(first, smallidx - 1)] // 2
+            smallnum = _XTC_MAGIC[smallidx] // 2
+            larger = _XTC_MAGIC[maxidx] // 2
+            head_smallidx = smallidx
+            bw = _BitWriter()
+            c = ints.copy()
+            i, prevrun = 0, -1
+            prev = np.zeros(3, np.int64)
+            while i < N:
+                is_small = 0
+                this = c[i]
+                if smallidx < maxidx and i >= 1 and np.all(np.abs(this - prev) < larger):
+                    is_smaller = 1
+                elif smallidx > minidx:
+                    is_smaller = -1
+                else:
+                    is_smaller = 0
+                if i + 1 < N and np.all(np.abs(c[i] - c[i + 1]) < smallnum):
+                    c[[i, i + 1]] = c[[i + 1, i]]              # the second atom is coded first (water: O between its H)
+                    this = c[i]
+                    is_small = 1
+                rel = this - lo
+                if bitsize == 0:
+                    for k in range(3):
+                        bw.put(bits3[k], rel[k])
+                else:
+                    bw.put3(bitsize, size, rel)
+                prev = this.copy()
+                i += 1
+                run = []
+                if is_small == 0 and is_smaller == -1:
+                    is_smaller = 0
+                while is_small and len(run) < 8 * 3:
+                    this = c[i]
+                    if is_smaller == -1 and int(((this - prev) ** 2).sum()) >= smaller * smaller:
+                        is_smaller = 0
+                    run.extend((this - prev + smallnum).tolist())
+                    prev = this.copy()
+                    i += 1
+                    is_small = 1 if i < N and np.all(np.abs(c[i] - prev) < smallnum) else 0
+                if len(run) != prevrun or is_smaller != 0:
+                    prevrun = len(run)
+                    bw.put(1, 1)
+                    bw.put(5, len(run) + is_smaller + 1)
+                else:
+                    bw.put(1, 0)
+                sizes = [_XTC_MAGIC[smallidx]] * 3
+                for k in range(0, len(run), 3):
+                    bw.put3(smallidx, sizes, run[k:k + 3])
+                if is_smaller != 0:
+                    smallidx += is_smaller
+                    if is_smaller < 0:
+                        smallnum = smaller
+                        smaller = _XTC_MAGIC[smallidx - 1] // 2
+                    else:
+                        smaller = smallnum
+                        smallnum = _XTC_MAGIC[smallidx] // 2
+            data = bw.bytes()
+            fh.write(struct.pack(">f", precision) + struct.pack(">iii", *[int(v) for v in lo]) + struct.pack(">iii", *[int(v) for v in hi])
+                     + struct.pack(">i", head_smallidx))
+            fh.write(struct.pack(">q", len(data)) if magic == 2023 else struct.pack(">i", len(data)))
+            fh.write(data + b"\0" * ((-len(data)) % 4))
+    return want
 
 class _MdcrdFile:
     """Amber ASCII trajectory (mdcrd): a title line, then per frame 3N coordinates in Fortran 10F8.3 (eight characters

@@ -286,6 +286,18 @@ int caviar_compact_frames_soa_host(const void* src, int64_t n_frames, int64_t fr
                                    int64_t x_off, int64_t y_off, int64_t z_off, const int32_t* atoms,
                                    int64_t n_sel, int32_t byte_swap, float* out);
 
+/* GROMACS XTC trajectories (the reference CLI advertises them, CAVIAR_Distances-Extractor.py:99, and leaves them to
+ * cpptraj): compressed integer coordinates, decoded on the host threads (cv_xtc.cu restates the published xdr3dfcoord
+ * algorithm of the xdrfile library).  `data` / `size`: the file image (e.g. a read-only memory map).
+ *   caviar_xtc_index: number of frames (< 0: CV_E_*), atom count in *n_atoms, byte offset of every frame in offsets[]
+ *                     when it has room for them (cap entries; NULL to count only).
+ *   caviar_xtc_decode_host: frames at offsets[0 .. n_frames) -> xyz_out [n_frames][n_sel][3] float32 = positions of the
+ *                     selected atoms (atoms == NULL: all) * scale, box_out [n_frames][9] = box vectors * scale or NULL
+ *                     (XTC is in nm: scale = 10 gives Angstrom). */
+int64_t caviar_xtc_index(const void* data, int64_t size, int64_t* offsets, int64_t cap, int32_t* n_atoms);
+int caviar_xtc_decode_host(const void* data, int64_t size, const int64_t* offsets, int64_t n_frames,
+                           const int32_t* atoms, int64_t n_sel, float scale, float* xyz_out, float* box_out);
+
 /* Host-side CSV row formatter for the Extractor output (CAVIAR_Distances-Extractor.py:147-151,196-198: one frame
  * column, then one distance column per pair).  Formats rows x cols float32 values as
  *     "<first_index + r*index_step>,<v>,<v>,...<EOL>"    with `decimals` fixed decimals (printf "%.Nf" rounding)

@@ -309,16 +309,21 @@ def test_trr_trajectories_and_gro_topology(ext, tmp_path, box, vel):
 
 
 def test_unsupported_inputs_fail_with_a_clear_message(ext, tmp_path):
-    """The formats the reference's help text lists but this reader does not take (Extractor:99) exit with [ERR],
+    """Formats this reader does not take, and damaged files, exit with [ERR],
     not with a scipy traceback; resSeq numbering needs a topology that carries residue numbers."""
     from caviar_b200 import trajio
-    for name, head in (("t.xtc", b"\x00\x00\x07\xcb" + b"\0" * 60),
-                       ("t4.nc", b"\x89HDF\r\n\x1a\n" + b"\0" * 60), ("t.foo", b"whatever")):
+    for name, head in (("t4.nc", b"\x89HDF\r\n\x1a\n" + b"\0" * 60), ("t.foo", b"whatever")):
         p = tmp_path / name
         p.write_bytes(head)
         with pytest.raises(SystemExit) as e:
             trajio.Trajectory(str(p))
         assert "[ERR] formato di traiettoria non supportato" in str(e.value), name
+    # XTC is read (tests/test_trajio_foreign.py); a damaged one is refused with a message, not mis-read
+    p = tmp_path / "t.xtc"
+    p.write_bytes(b"\x00\x00\x07\xcb" + b"\0" * 60)
+    with pytest.raises(SystemExit) as e:
+        trajio.Trajectory(str(p))
+    assert "[ERR]" in str(e.value) and "XTC" in str(e.value)
     names, labels, first = ["N", "CA", "C"] * 4, ["ALA", "GLY", "SER", "THR"], [0, 3, 6, 9]
     top_path = tmp_path / "s.prmtop"
     trajio.write_prmtop(str(top_path), names, labels, first)

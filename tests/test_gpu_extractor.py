@@ -92,6 +92,43 @@ def test_extractor_cli_against_oracle(tmp_path, capsys, box, stride, fmt):
     assert s["frame_score_weighted"] == orc.weighted_frame_scores(d.astype(np.float64) < 8.0, s["pair_weights"]).tolist()
 
 
+@pytest.mark.parametrize("box", [None, "ortho"])
+def test_extractor_cli_reads_gromacs_xtc_and_gro(tmp_path, capsys, box):
+    """GROMACS inputs end to end: .gro topology + compressed .xtc trajectory (nm, 0.001 nm precision).  The positions
+    the reader must deliver are the rounded ones the file holds; on those the no-box distances are bit-exact."""
+    from caviar_b200 import extractor, trajio
+    rng = np.random.default_rng(2)
+    n_res, T = 40, 31
+    res3 = ["ASP", "GLU", "ALA", "GLY", "SER"]
+    L = np.array([40.0, 35.0, 30.0])                                   # 4.0 / 3.5 / 3.0 nm: exact in float32
+    n_atoms = 3 * n_res
+    base = np.cumsum(rng.normal(0, 1.5, size=(n_atoms, 3)), axis=0) % L
+    xyz = ((base[None] + rng.normal(0, 0.4, size=(T, n_atoms, 3))) % L).astype(np.float32)
+    gro = tmp_path / "sys.gro"
+    lines = ["toy", str(n_atoms)]
+    for a in range(n_atoms):
+        r = a // 3
+        lines.append("%5d%-5s%5s%5d%8.3f%8.3f%8.3f" % (r + 1, res3[r % 5], ("N", "CA", "C")[a % 3], a + 1, *(xyz[0, a] / 10)))
+    lines.append("%10.5f%10.5f%10.5f" % tuple(L / 10))
+    gro.write_text("\n".join(lines) + "\n")
+    xtc = str(tmp_path / "traj.xtc")
+    kept = trajio.write_xtc(xtc, xyz / np.float32(10.0), np.diag(L / 10) if box else None) * np.float32(10.0)
+    out, npy = tmp_path / "o.csv", tmp_path / "o.npy"
+    labels = {i: f"{res3[i % 5]}{i + 1}" for i in range(n_res)}
+    sel = [(0, 9), (3, 39), (20, 21)]
+    rc = extractor.main(["--top", str(gro), "--traj", xtc, "--pairs", ",".join(f"{labels[a]}-{labels[b]}" for a, b in sel),
+                         "--stride", "2", "--out", str(out), "--npy-out", str(npy)])
+    assert rc == 0 and "[DONE] Salvato CSV" in capsys.readouterr().out
+    frames = kept[::2]
+    pairs = [(3 * a + 1, 3 * b + 1) for a, b in sel]
+    d = np.load(npy)
+    if box is None:
+        assert d.tobytes() == orc.pair_distances(frames, pairs, n_jobs=1).tobytes()
+    else:
+        want = orc.pbc_pair_distances(frames, pairs, np.broadcast_to(L, (len(frames), 3)))
+        assert np.abs(d - want).max() <= 1e-4
+
+
 def test_extractor_error_paths(tmp_path):
     from caviar_b200 import extractor
     top, nc, xyz, L, ca, labels = _system(tmp_path, None)

@@ -174,3 +174,120 @@ def test_mdcrd_assembled_from_the_format_description(trajio, tmp_path, n, with_b
         trajio.Trajectory(str(p))                                        # no atom count, no guess
     with pytest.raises(ValueError):
         trajio.Trajectory(str(p), n_atoms=n + 1)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# XTC: GROMACS compressed trajectory (xdrfile's xdr3dfcoord).  Per frame, XDR: magic 1995 (2023: 64-bit byte count),
+# natoms, step, time, box (3x3, nm), natoms; for natoms <= 9 plain floats; otherwise precision, minint[3], maxint[3],
+# smallidx, byte count, and a most-significant-bit-first bit stream: per atom the three integers (x * precision - minint)
+# as ONE number in the mixed radix (sizeint) cut into 8-bit groups, LEAST significant group first, the last group with the
+# remaining bits; then a 1-bit "run changed" flag (+ 5 bits: run length * 3 + (smaller/same/larger radix) code) and,
+# inside a run, one small number per atom: offsets (+ smallnum) from the previous atom in the radix magicints[smallidx],
+# smallidx bits each; the first two atoms of a run are stored swapped.  The fixture below is assembled with Python's big
+# integers and string formatting -- nothing of trajio's writer -- and holds a run that is written out by hand.
+# ---------------------------------------------------------------------------------------------------------
+def _bits(value, n):
+    return format(int(value), "0{}b".format(n)) if n else ""
+
+
+def _groups(value, nbits):
+    out = ""
+    while nbits > 8:
+        out += _bits(value & 0xFF, 8)
+        value >>= 8
+        nbits -= 8
+    return out + _bits(value, nbits)
+
+
+def _xtc_frame(ints, precision, box, step, runs=()):
+    """`ints` (N, 3) integer positions; `runs`: indices i such that atoms i, i+1, i+2 form one run of two small offsets
+    (i+1 and i+2 relative to their predecessors), written the way the format asks: atom i+1 first (large), then atom i
+    and atom i+2 as small numbers."""
+    N = len(ints)
+    lo, hi = ints.min(axis=0), ints.max(axis=0)
+    size = [int(v) for v in (hi - lo + 1)]
+    bitsize = (size[0] * size[1] * size[2]).bit_length()
+    smallidx = 21                                   # radix 128 (magicints[21]), offsets within +-64, 21 bits per atom
+    radix, smallnum = 128, 64
+    stream, i, prevrun = "", 0, -1
+    while i < N:
+        if i in runs:
+            first, second, third = ints[i + 1], ints[i], ints[i + 2]          # stored order: swapped pair, then the third
+            rel = first - lo
+            stream += _groups((int(rel[0]) * size[1] + int(rel[1])) * size[2] + int(rel[2]), bitsize)
+            stream += "1" + _bits(6 + 1, 5) if prevrun != 6 else "0"          # run of 2 atoms = 6 numbers, same radix
+            prevrun = 6
+            for cur, prev in ((second, first), (third, second)):
+                o = cur - prev + smallnum
+                assert (o >= 0).all() and (o < radix).all()
+                stream += _groups((int(o[0]) * radix + int(o[1])) * radix + int(o[2]), smallidx)
+            i += 3
+        else:
+            rel = ints[i] - lo
+            stream += _groups((int(rel[0]) * size[1] + int(rel[1])) * size[2] + int(rel[2]), bitsize)
+            stream += "1" + _bits(0 + 1, 5) if prevrun != 0 else "0"
+            prevrun = 0
+            i += 1
+    stream += "0" * ((-len(stream)) % 8)
+    data = bytes(int(stream[k:k + 8], 2) for k in range(0, len(stream), 8))
+    head = struct.pack(">iiif", 1995, N, step, 0.5 * step) + np.asarray(box, ">f4").tobytes() + struct.pack(">i", N)
+    body = struct.pack(">f", precision) + struct.pack(">6i", *[int(v) for v in lo], *[int(v) for v in hi]) + struct.pack(">ii", smallidx, len(data))
+    return head + body + data + b"\0" * ((-len(data)) % 4)
+
+
+def test_xtc_assembled_from_the_format_description(trajio, tmp_path):
+    rng = np.random.default_rng(3)
+    N, T = 23, 3
+    box = np.array([[3.0, 0, 0], [0.5, 3.1, 0], [0.25, -0.5, 2.9]], np.float32)            # triclinic, nm
+    frames, blob = [], b""
+    for t in range(T):
+        ints = rng.integers(-1500, 4200, size=(N, 3))
+        for r in (4, 11):                                  # three atoms within +-40 of each other: a hand-written run
+            ints[r + 1] = ints[r] + rng.integers(-40, 40, size=3)
+            ints[r + 2] = ints[r + 1] + rng.integers(-20, 20, size=3)
+        frames.append(ints)
+        blob += _xtc_frame(ints, 1000.0, box, t, runs=(4, 11))
+    path = tmp_path / "hand.xtc"
+    path.write_bytes(blob)
+    tr = trajio.Trajectory(str(path))
+    assert (tr.n_frames, tr.n_atoms, tr.box_kind()) == (T, N, "triclinic")
+    want = np.stack(frames).astype(np.float32) * np.float32(1.0 / 1000.0) * np.float32(10.0)   # nm -> Angstrom
+    assert np.array_equal(tr.coords(0, T), want)
+    sel = np.array([12, 0, 5, 22], np.int32)
+    assert np.array_equal(tr.coords_of(sel, 1, 3), want[1:3][:, sel])
+    np.testing.assert_allclose(tr.cell(0, T), np.broadcast_to(box * 10.0, (T, 3, 3)), rtol=1e-6)
+    # few atoms: plain big-endian floats
+    x = rng.random((2, 5, 3)).astype(np.float32)
+    small = b"".join(struct.pack(">iiif", 1995, 5, t, 0.0) + np.zeros(9, ">f4").tobytes() + struct.pack(">i", 5) + x[t].astype(">f4").tobytes()
+                     for t in range(2))
+    p2 = tmp_path / "small.xtc"
+    p2.write_bytes(small)
+    t2 = trajio.Trajectory(str(p2))
+    assert t2.n_frames == 2 and not t2.has_box and np.array_equal(t2.coords(0, 2), x * np.float32(10.0))
+    # damaged files are refused, not mis-read
+    bad = tmp_path / "bad.xtc"
+    bad.write_bytes(blob[:-8])
+    with pytest.raises(SystemExit) as e:
+        trajio.Trajectory(str(bad))
+    assert "[ERR]" in str(e.value) and "XTC" in str(e.value)
+
+
+def test_xtc_writer_reader_round_trip_with_runs_and_radix_changes(trajio, tmp_path):
+    """trajio.write_xtc follows the compressor of the format (runs, swapped water atoms, adaptive radix); the native
+    reader must give back exactly the rounded positions, whatever mixture the data produces."""
+    rng = np.random.default_rng(0)
+    T, nw = 4, 300
+    centers = rng.random((T, nw, 1, 3)) * 5.0
+    water = centers + rng.normal(0, 0.05, size=(T, nw, 3, 3))
+    chain = np.cumsum(rng.normal(0, 0.08, size=(T, 150, 3)), axis=1) + 2.5          # a polymer: long runs of close atoms
+    far = rng.random((T, 40, 3)) * 5.0
+    xyz = np.concatenate([far[:, :10], water.reshape(T, -1, 3), chain, far[:, 10:]], axis=1).astype(np.float32)
+    box = np.diag([5.0, 5.1, 5.2]).astype(np.float32)
+    for magic, scale in ((1995, 1.0), (2023, 1.0), (1995, 9000.0)):                # last: ranges too wide for one number
+        path = str(tmp_path / f"rt_{magic}_{int(scale)}.xtc")
+        want = trajio.write_xtc(path, xyz * np.float32(scale), box, magic=magic)
+        tr = trajio.Trajectory(path)
+        assert (tr.n_frames, tr.n_atoms, tr.box_kind()) == (T, xyz.shape[1], "ortho")
+        assert np.array_equal(tr.coords(0, T), want * np.float32(10.0))
+        assert np.abs(want - xyz * np.float32(scale)).max() <= 0.0005 * max(1.0, scale / 64)
+        tr.close()
