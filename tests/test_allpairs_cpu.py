@@ -47,3 +47,20 @@ def test_lists_that_are_not_the_reference_list_stay_on_the_generic_kernel(cb):
 def test_environment_switch_disables_the_flavour(cb, monkeypatch):
     monkeypatch.setenv("CAVIAR_NO_ALLPAIRS", "1")
     assert cb.FeaturePlan(1000, cb.all_pairs(1000, 5), None, describe_only_sms=148).info["mode_name"] == "zerocopy"
+
+
+def test_random_geometries(cb):
+    """Any selection size (multiple of 4) and separation the planner accepts: the geometry check holds."""
+    rng = np.random.default_rng(7)
+    seen = 0
+    for _ in range(60):
+        n = int(rng.integers(150, 700)) * 4
+        m = int(rng.integers(1, 200))
+        plan = cb.FeaturePlan(n, cb.all_pairs(n, m), None, describe_only_sms=int(rng.choice([148, 132, 8])))
+        st = plan.allpairs_check()
+        if plan.info["mode_name"] == "allpairs":
+            assert st["n_tiles"] > 0 and st["max_tile_atoms"] <= 700 and st["smem_bytes"] <= 110 * 1024, (n, m, st)
+            seen += 1
+        else:
+            assert st["n_tiles"] == 0
+    assert seen >= 20

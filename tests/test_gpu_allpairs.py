@@ -192,3 +192,60 @@ def test_host_entry_point_and_operator_take_the_flavour(cb):
     assert np.array_equal(res["occupancy"], flags_want.sum(axis=0))
     got = cb.compute_distances_parallel(xh[:9], [tuple(p) for p in pairs.tolist()])
     assert got.tobytes() == want[:9].tobytes()
+
+
+def test_packed_float64_aggregates_and_frame_sharding(cb):
+    """The multi-GPU exchange format: occupancy as float64 next to the moments in one buffer (added in place by the kernel);
+    two frame shards accumulated into the same buffer equal the single run -- integers exactly, moments to rounding."""
+    import torch
+    rng = np.random.default_rng(11)
+    n, T = 1000, 301
+    xh = _frames(rng, T, n, scale=1.0)
+    x = torch.from_numpy(xh).cuda()
+    with cb.FeaturePlan(n, cb.all_pairs(n, 5), None, pair_cutoff=8.5) as plan:
+        _, ref = _run(cb, plan, x, want=("flags",))
+        buf, agg = plan.new_packed_aggregates()
+        out = plan.alloc_outputs(T, want=("score",))
+        plan.run(x[:130], None, out=out, aggregates=agg, n_frames=130)
+        plan.run(x[130:], None, out=plan.alloc_outputs(T - 130, want=("score",)), aggregates=agg)
+        torch.cuda.synchronize()
+        F = plan.F
+        assert torch.equal(buf[:F].to(torch.int64), ref.occupancy)
+        assert torch.allclose(buf[F:2 * F], ref.sum, rtol=1e-13, atol=0) and torch.allclose(buf[2 * F:], ref.sumsq, rtol=1e-13, atol=0)
+        lean_buf, lean = plan.new_packed_aggregates(moments=False)
+        plan.run(x, None, out=plan.alloc_outputs(T, want=("flags",)), aggregates=lean)
+        torch.cuda.synchronize()
+        assert torch.equal(lean_buf.to(torch.int64), ref.occupancy)
+
+
+def test_random_selections_separations_and_grids(cb):
+    """Randomised: selection size, minimum separation, frame count, grid size, cut-off, outputs -- against the reference
+    arithmetic (bits) and numpy aggregates."""
+    import torch
+    rng = np.random.default_rng(2024)
+    done = 0
+    for trial in range(40):
+        n = int(rng.integers(176, 420)) * 4
+        m = int(rng.integers(1, 80))
+        T = int(rng.integers(1, 90))
+        pairs = cb.all_pairs(n, m)
+        n_ctas = int(rng.choice([0, 0, 3, 17, 64]))
+        cut = float(rng.uniform(5.0, 25.0))
+        with cb.FeaturePlan(n, pairs, None, pair_cutoff=cut, n_ctas=n_ctas) as plan:
+            if plan.info["mode_name"] != "allpairs":
+                continue
+            xh = _frames(rng, T, n, scale=float(rng.uniform(0.1, 2.0)))
+            lean = bool(rng.integers(0, 2))
+            want_out = ("flags", "score") if lean else ("dist", "flags", "score")
+            out, agg = _run(cb, plan, torch.from_numpy(xh).cuda(), want=want_out, moments=not lean)
+        want = orc.pair_distances_f32_steps(xh, pairs[:, 0], pairs[:, 1])
+        flags_want = orc.contact_flags(want, cut)
+        fp, _ = cb.unpack_flags(out.flags.cpu().numpy(), len(pairs), 0)
+        assert np.array_equal(fp, flags_want), (n, m, T, n_ctas, lean)
+        assert np.array_equal(out.score.cpu().numpy(), flags_want.sum(axis=1))
+        assert np.array_equal(agg.occupancy.cpu().numpy(), flags_want.sum(axis=0))
+        if not lean:
+            assert out.dist.cpu().numpy().tobytes() == want.tobytes(), (n, m, T, n_ctas)
+            np.testing.assert_allclose(agg.sum.cpu().numpy(), want.astype(np.float64).sum(axis=0), rtol=1e-12)
+        done += 1
+    assert done >= 10
