@@ -266,7 +266,8 @@ class DeviceWorkload:
     compact frames for zero-copy / direct plans.  ``step(n)`` runs the whole device path over n logical frames by
     cycling over the resident block (the big configs do not fit; every launch streams the block from HBM)."""
 
-    def __init__(self, cb, syn, cfg_id, block_frames, dev, seed=0, want=("dist", "angle", "flags", "score"), moments=True):
+    def __init__(self, cb, syn, cfg_id, block_frames, dev, seed=0, want=("dist", "angle", "flags", "score"), moments=True,
+                 aggregates=True):
         import torch
         self.torch = torch
         self.top = syn.make_topology(cfg_id)
@@ -296,7 +297,7 @@ class DeviceWorkload:
         self.out = self.plan.alloc_outputs(block_frames, want=want, device=dev)
         # ONE float64 buffer [occupancy | sum | sumsq]: the kernel accumulates the counts as float64 (exact < 2^53), so
         # the multi-GPU exchange is a single all-reduce of this buffer, nothing to pack
-        self.agg_buf, self.agg = self.plan.new_packed_aggregates(dev, moments=moments)
+        self.agg_buf, self.agg = self.plan.new_packed_aggregates(dev, moments=moments) if aggregates else (None, None)
         self.ws = self.plan.new_workspace(dev)
         self.launches = 0
         # algorithmic bytes per frame of THIS output selection (a disabled store leaves B_alg)
@@ -305,7 +306,8 @@ class DeviceWorkload:
                           + (4 * self.plan.W if self.out.flags is not None else 0) + (4 if self.out.score is not None else 0))
 
     def zero(self):
-        self.agg_buf.zero_()
+        if self.agg_buf is not None:
+            self.agg_buf.zero_()
 
     def step(self, n_frames=None):
         n_frames = self.block if n_frames is None else n_frames
@@ -581,7 +583,8 @@ def main():
     torch.cuda.empty_cache()
 
     # ---- BASELINE config 5 as BASELINE states it: its 500 000 frames split over the N ranks + the NCCL reduce ----
-    def config_run(cfg_id, frames_total, block, reps, want=("dist", "angle", "flags", "score"), moments=True, shard=False):
+    def config_run(cfg_id, frames_total, block, reps, want=("dist", "angle", "flags", "score"), moments=True, shard=False,
+                   aggregates=True):
         """Whole-job time of one BASELINE shape: frames_total logical frames (split over the ranks when shard), cycled
         over a resident block of `block` frames per rank; every launch streams the block from HBM (block >> L2)."""
         lo, hi = (0, frames_total)
@@ -589,7 +592,8 @@ def main():
             from caviar_b200.sharding import frame_shard
             lo, hi = frame_shard(frames_total, rank, world)
         mine = hi - lo
-        w = DeviceWorkload(cb, syn, cfg_id, max(1, min(block, mine)), dev, seed=7000 + 1000 * rank, want=want, moments=moments)
+        w = DeviceWorkload(cb, syn, cfg_id, max(1, min(block, mine)), dev, seed=7000 + 1000 * rank, want=want, moments=moments,
+                           aggregates=aggregates)
 
         def one():
             w.zero()
@@ -607,12 +611,12 @@ def main():
         alg = w.alg_bytes * mine                               # per GPU
         res = {"workload": f"config {cfg_id}: {w.cfg.description}", "frames_total": frames_total, "frames_per_gpu": mine,
                "resident_block_frames": w.block, "launches_per_step": w.launches, "plan_mode": w.info["mode_name"],
-               "outputs": list(want) + (["occupancy", "sum", "sumsq"] if moments else ["occupancy"]),
+               "outputs": list(want) + ((["occupancy", "sum", "sumsq"] if moments else ["occupancy"]) if aggregates else []),
                "ms": ms, "value": evals / (ms * 1e-3), "unit": UNIT,
                "algorithmic_bytes_per_frame": w.alg_bytes, "roofline_frac_per_gpu": alg / (ms * 1e-3) / 1e9 / peak,
                "input": "raw float32 frames in plan order" if w.info["mode_name"] == "staged" else "the caller's frames as they are (no K0 in this mode)"}
-        occ_total = int(w.agg.occupancy.sum())
-        res["occupancy_sum"] = occ_total
+        if aggregates:
+            res["occupancy_sum"] = int(w.agg.occupancy.sum())
         w.close()
         torch.cuda.empty_cache()
         return res
@@ -634,6 +638,10 @@ def main():
         c4["note"] = ("all-pairs list on its own kernel (cv::allpairs_kernel, 2-D tiles), distances emitted: 1.98 MB of stores per frame "
                       "against 12 KB of input -- bound by the LSU / store path of the SMs and by HBM write locality (DESIGN 4a)")
         all_configs["cfg4_distances_emitted"] = c4
+        c4d = config_run(4, syn.CONFIGS[4].n_frames, 8192, 2, want=("dist",), aggregates=False)
+        c4d["note"] = ("the reference operator's own workload on this shape: compute_distances_parallel (CAVIAR-1.0.py:110-122) "
+                       "emits the (T, P) distance matrix and nothing else")
+        all_configs["cfg4_distance_matrix_only"] = c4d
         c4l = config_run(4, syn.CONFIGS[4].n_frames, 8192, 2, want=("flags", "score"), moments=False)
         # issue roofline: warp instructions per frame (ncu, profiles/traffic.json) x frames/s / (SMs x 4 schedulers x clock)
         rec4 = profile_record("cfg4_lean")

@@ -408,7 +408,8 @@ template <bool LEAN, bool FAST>
 static cudaError_t launch_allpairs(const CvPlan* plan, const ApParams& ap, cudaStream_t st) {
     if (ap.n_tiles <= 0) return cudaSuccess;
     auto kern = allpairs_kernel<LEAN, FAST>;
-    const int smem = plan->hp.ap.smem_bytes;
+    const int occ = (LEAN && FAST) ? kApLeanOccupancy : 2;
+    const int smem = ap.n_stages * ap.stage_floats * 4 + (2 * kMaxStages * 8 + kMaxStages * 24);
     static int granted[64] = {0};
     const int dev = plan->device & 63;
     if (smem > granted[dev]) {
@@ -416,7 +417,7 @@ static cudaError_t launch_allpairs(const CvPlan* plan, const ApParams& ap, cudaS
         if (e != cudaSuccess) return e;
         granted[dev] = smem;
     }
-    kern<<<plan->hp.ap.n_ctas, kConsumerThreads + kProducerThreads, smem, st>>>(ap);
+    kern<<<plan->hp.ap.n_ctas / 2 * occ, kConsumerThreads + kProducerThreads, smem, st>>>(ap);
     return cudaGetLastError();
 }
 
@@ -563,6 +564,13 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
         ApParams gen = ap;
         gen.tiles = ap.tiles + n_fast; gen.n_tiles = ap.n_tiles - n_fast; gen.queue = ap.queue + 16; gen.seq = ap.seq + n_fast;
         ap.n_tiles = n_fast;
+        if (lean && kApLeanOccupancy > 2) {
+            // three CTAs per SM: three rings must fit in shared memory
+            while (ap.frames_per_stage > 1 && kApLeanOccupancy * (ap.n_stages * ap.stage_floats * 4 + 1024) > 220 * 1024) {
+                ap.stage_floats = ap.stage_floats / ap.frames_per_stage * (ap.frames_per_stage / 2);
+                ap.frames_per_stage /= 2;
+            }
+        }
         e = lean ? launch_allpairs<true, true>(plan, ap, st) : launch_allpairs<false, true>(plan, ap, st);
         if (e == cudaSuccess) e = lean ? launch_allpairs<true, false>(plan, gen, st) : launch_allpairs<false, false>(plan, gen, st);
         if (e != cudaSuccess) return fail(CV_E_CUDA, std::string("allpairs_kernel launch: ") + cudaGetErrorString(e));

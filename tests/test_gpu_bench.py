@@ -40,7 +40,7 @@ def test_bench_line_contract():
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     # staging is inside the number: the timed input is raw frames in plan order, and the caller-order / other-config legs exist
     assert "no staging kernel" in d["config"]["input"] and d["caller_order_input"]["k0_ms"] > 0
-    assert set(d["all_configs"]) == {"cfg1", "cfg2", "cfg4_distances_emitted", "cfg4_contact_map", "cfg5"}
+    assert set(d["all_configs"]) == {"cfg1", "cfg2", "cfg4_distances_emitted", "cfg4_distance_matrix_only", "cfg4_contact_map", "cfg5"}
     for name, c in d["all_configs"].items():
         assert c["value"] > 0 and 0 < c["roofline_frac_per_gpu"] < 1.2, name
     assert d["config5_sharded"]["frames_total"] == 500000 and d["config5_sharded"]["occupancy_sum"] > 0
