@@ -207,14 +207,21 @@ extern "C" int64_t caviar_plan_allpairs_check(const CvPlanDesc* desc, int32_t n_
     for (size_t c = 0; c < ap.tiles.size(); ++c) {
         const ApTile& t = ap.tiles[c];
         const std::string at = " (tile " + std::to_string(c) + ")";
-        if (t.a0 % 4 || t.n0 % 4 || t.a1 % 4 || t.n1 % 4 || t.n0 < 4 || t.a0 < 0 || t.a0 + t.n0 > n) return fail(CV_E_INVALID, "atom range 0 misaligned or out of the frame" + at);
+        if (t.a0 % 4 || t.n0 % 4 || t.a1 % 4 || t.n1 % 4 || t.a2 % 4 || t.n2 % 4 || t.n0 < 4 || t.a0 < 0 || t.a0 + t.n0 > n)
+            return fail(CV_E_INVALID, "atom range 0 misaligned or out of the frame" + at);
         if (t.n1 > 0 && (t.a1 < t.a0 + t.n0 || t.a1 + t.n1 > n)) return fail(CV_E_INVALID, "atom range 1 overlaps range 0 or leaves the frame" + at);
-        if (3 * (t.n0 + t.n1) * ap.frames_per_stage > ap.stage_floats) return fail(CV_E_INVALID, "stage too small" + at);
-        max_atoms = std::max<int64_t>(max_atoms, t.n0 + t.n1); sum_atoms += t.n0 + t.n1;
-        if (getenv("CAVIAR_AP_DUMP") && t.n0 + t.n1 > atoi(getenv("CAVIAR_AP_DUMP")))
-            fprintf(stderr, "tile %zu fast_mask %x atoms [%d,+%d) [%d,+%d) blk0 %d..%d blk1 %d..%d\n", c, t.fast_mask, t.a0, t.n0, t.a1, t.n1,
-                    t.blk[0][0], t.blk[0][6], t.blk[1][0], t.blk[1][6]);
-        auto atom_of = [&](int off) { const int a = off / 3; return a < t.n0 ? t.a0 + a : t.a1 + (a - t.n0); };
+        if (t.n2 > 0 && (t.n1 <= 0 || t.a2 < t.a1 + t.n1 || t.a2 + t.n2 > n)) return fail(CV_E_INVALID, "atom range 2 overlaps range 1 or leaves the frame" + at);
+        const int tile_atoms = t.n0 + t.n1 + t.n2;
+        if (3 * tile_atoms * ap.frames_per_stage > ap.stage_floats) return fail(CV_E_INVALID, "stage too small" + at);
+        max_atoms = std::max<int64_t>(max_atoms, tile_atoms); sum_atoms += tile_atoms;
+        if (getenv("CAVIAR_AP_DUMP") && tile_atoms > atoi(getenv("CAVIAR_AP_DUMP")))
+            fprintf(stderr, "tile %zu fast_mask %x atoms [%d,+%d) [%d,+%d) [%d,+%d) blk0 %d..%d blk1 %d..%d\n", c, t.fast_mask, t.a0, t.n0, t.a1, t.n1,
+                    t.a2, t.n2, t.blk[0][0], t.blk[0][6], t.blk[1][0], t.blk[1][6]);
+        auto atom_of = [&](int off) {
+            const int a = off / 3;
+            return a < t.n0 ? t.a0 + a : (a < t.n0 + t.n1 ? t.a1 + (a - t.n0) : t.a2 + (a - t.n0 - t.n1));
+        };
+        const bool shared = (int)c < ap.n_shared_tiles;
         for (int w = 0; w < kApWarps; ++w) {
             const bool fast = (t.fast_mask >> w) & 1;
             // the fast kernel runs tiles [0, n_fast_tiles): there a warp has two whole windows or none at all
@@ -233,12 +240,12 @@ extern "C" int64_t caviar_plan_allpairs_check(const CvPlanDesc* desc, int32_t n_
                     if (k < 0 || k >= P) return fail(CV_E_INVALID, "slot beyond the list" + at);
                     if (seen[k]++) return fail(CV_E_INVALID, "pair " + std::to_string(k) + " evaluated twice" + at);
                     int io = th.ioff[q], jo = th.joff[q];
-                    if (fast) {                       // what ap_fast_frame reads
-                        io = th.ioff[kApSlots * win]; jo = th.joff[kApSlots * win] + 96 * m;
+                    if (fast) {                       // what ap_fast_frame / ap_shared_frame read
+                        io = th.ioff[kApSlots * win]; jo = th.joff[shared ? 0 : kApSlots * win] + 96 * m;
                         if (i_uniform[win] < 0) i_uniform[win] = io;
                         if (io != i_uniform[win]) return fail(CV_E_INVALID, "fast warp is not uniform in i" + at);
                     }
-                    if (io < 0 || jo < 0 || io % 3 || jo % 3 || io / 3 >= t.n0 + t.n1 || jo / 3 >= t.n0 + t.n1)
+                    if (io < 0 || jo < 0 || io % 3 || jo % 3 || io / 3 >= tile_atoms || jo / 3 >= tile_atoms)
                         return fail(CV_E_INVALID, "offset outside the tile's block" + at);
                     if (atom_of(io) != hp.pairs[2 * k] || atom_of(jo) != hp.pairs[2 * k + 1])
                         return fail(CV_E_INVALID, "pair " + std::to_string(k) + " resolves to the wrong atoms" + at);
@@ -404,11 +411,11 @@ static cudaError_t launch_features(const CvPlan* plan, const RunParams& rp, cuda
 }
 
 
-template <bool LEAN, bool FAST>
+template <bool LEAN, int KIND>
 static cudaError_t launch_allpairs(const CvPlan* plan, const ApParams& ap, cudaStream_t st) {
     if (ap.n_tiles <= 0) return cudaSuccess;
-    auto kern = allpairs_kernel<LEAN, FAST>;
-    const int occ = (LEAN && FAST) ? kApLeanOccupancy : 2;
+    auto kern = allpairs_kernel<LEAN, KIND>;
+    const int occ = (LEAN && KIND != AP_GENERAL) ? kApLeanOccupancy : 2;
     const int smem = ap.n_stages * ap.stage_floats * 4 + (2 * kMaxStages * 8 + kMaxStages * 24);
     static int granted[64] = {0};
     const int dev = plan->device & 63;
@@ -538,7 +545,7 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
     }
     rp.pair_thr = hp.pair_thr; rp.pair_thr2 = hp.pair_thr2; rp.hb_dthr = hp.hb_dthr; rp.hb_athr = hp.hb_athr;
 
-    CV_CUDA(cudaMemsetAsync(rp.queue, 0, 128, st));       // work counters (the all-pairs flavour keeps two, 64 bytes apart)
+    CV_CUDA(cudaMemsetAsync(rp.queue, 0, kQueueBytes, st));       // work counters (the all-pairs flavour keeps three, 64 bytes apart)
     if (rp.score) CV_CUDA(cudaMemsetAsync(rp.score, 0, sizeof(int32_t) * n_frames, st));
 
     cudaError_t e;
@@ -558,23 +565,30 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
             ap.sum = agg->sum; ap.sq = agg->sumsq;
         }
         ap.pair_thr = hp.pair_thr; ap.pair_thr2 = hp.pair_thr2;
-        // fast tiles (listed first) with the fast flavour, the rest with the general one; the fast body stores the distance
+        // tiles are listed [shared columns | fast | general], one instantiation each; the first two store the distance
         // matrix unconditionally, so a run that wants moments without it takes the general flavour throughout
-        const int n_fast = (lean || rp.dist) ? hp.ap.n_fast_tiles : 0;
-        ApParams gen = ap;
-        gen.tiles = ap.tiles + n_fast; gen.n_tiles = ap.n_tiles - n_fast; gen.queue = ap.queue + 16; gen.seq = ap.seq + n_fast;
-        ap.n_tiles = n_fast;
+        const bool direct = lean || rp.dist;
+        const int n_shared = direct ? hp.ap.n_shared_tiles : 0, n_fast = direct ? hp.ap.n_fast_tiles : 0;
+        ApParams part[3] = {ap, ap, ap};
+        const int first[4] = {0, n_shared, n_fast, ap.n_tiles};
+        for (int k = 0; k < 3; ++k) {
+            part[k].tiles = ap.tiles + first[k]; part[k].n_tiles = first[k + 1] - first[k];
+            part[k].queue = ap.queue + 16 * k; part[k].seq = ap.seq + first[k];
+        }
         if (lean && kApLeanOccupancy > 2) {
             // three CTAs per SM: three rings must fit in shared memory
-            while (ap.frames_per_stage > 1 && kApLeanOccupancy * (ap.n_stages * ap.stage_floats * 4 + 1024) > 220 * 1024) {
-                ap.stage_floats = ap.stage_floats / ap.frames_per_stage * (ap.frames_per_stage / 2);
-                ap.frames_per_stage /= 2;
-            }
+            for (int k = 0; k < 2; ++k)
+                while (part[k].frames_per_stage > 1 && kApLeanOccupancy * (part[k].n_stages * part[k].stage_floats * 4 + 1024) > 220 * 1024) {
+                    part[k].stage_floats = part[k].stage_floats / part[k].frames_per_stage * (part[k].frames_per_stage / 2);
+                    part[k].frames_per_stage /= 2;
+                }
         }
-        e = lean ? launch_allpairs<true, true>(plan, ap, st) : launch_allpairs<false, true>(plan, ap, st);
-        if (e == cudaSuccess) e = lean ? launch_allpairs<true, false>(plan, gen, st) : launch_allpairs<false, false>(plan, gen, st);
+        e = lean ? launch_allpairs<true, AP_SHARED>(plan, part[0], st) : launch_allpairs<false, AP_SHARED>(plan, part[0], st);
+        if (e == cudaSuccess) e = lean ? launch_allpairs<true, AP_FAST>(plan, part[1], st) : launch_allpairs<false, AP_FAST>(plan, part[1], st);
+        if (e == cudaSuccess) e = lean ? launch_allpairs<true, AP_GENERAL>(plan, part[2], st) : launch_allpairs<false, AP_GENERAL>(plan, part[2], st);
+        for (int k = 0; k < 3; ++k) g_launches += part[k].n_tiles > 0 ? 1 : 0;
+        g_launches -= 1;                                   // (one launch is counted below)
         if (e != cudaSuccess) return fail(CV_E_CUDA, std::string("allpairs_kernel launch: ") + cudaGetErrorString(e));
-        g_launches += (n_fast > 0 && gen.n_tiles > 0) ? 1 : 0;
     } else {
     // TMA ring (plan-order blocks or whole small frames) unless the plan gathers from the caller's frames
     const bool pipe = hp.mode != CV_MODE_DIRECT;

@@ -29,6 +29,7 @@ enum : int {
 };
 
 enum : int { KIND_PAIR = 0, KIND_TRIPLET = 1 };
+enum : int { AP_SHARED = 0, AP_FAST = 1, AP_GENERAL = 2 };   // flavours of allpairs_kernel, tiles listed in this order
 
 // One column tile = a contiguous slice of features evaluated by one CTA at a time.
 struct TileDesc {
@@ -93,7 +94,8 @@ struct ApTile {
     int32_t blk[2][kApWarps];   // window index of warp w (first / second window), -1 = none
     int32_t fast_mask;          // bit w: both windows of warp w are whole single-row windows
     int32_t a0, n0;             // atoms [a0, a0 + n0) of the frame (multiples of 4) ...
-    int32_t a1, n1;             // ... and [a1, a1 + n1), n1 = 0: one range
+    int32_t a1, n1;             // ... [a1, a1 + n1) ...
+    int32_t a2, n2;             // ... and [a2, a2 + n2); n = 0: range unused (ranges ascending, disjoint)
     int32_t reserved;
 };
 

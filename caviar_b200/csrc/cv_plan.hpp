@@ -27,7 +27,7 @@ struct ApHost {
     std::vector<int32_t> row_off;       // [n_rows + 1] first pair of row i
     std::vector<int32_t> row_of_word;   // [ceil(P / 32)] row of pair 32 w
     std::vector<ApTile> tiles;          // fast tiles first, general tiles last (the queue hands the last ones out first)
-    int n_fast_windows = 0, n_windows = 0, n_fast_tiles = 0;
+    int n_fast_windows = 0, n_windows = 0, n_shared_tiles = 0, n_fast_tiles = 0;   // tiles: [shared | fast | general], n_fast_tiles counts the first two
     int frames_per_stage = 0, n_stages = 0, stage_floats = 0, smem_bytes = 0, occupancy = 2, n_ctas = 0;
 };
 
@@ -397,7 +397,7 @@ inline void build_allpairs(HostPlan& hp) {
     // windows: fast = whole and inside one row
     const int nb = (int)((P + kApWindow - 1) / kApWindow);
     ap.n_windows = nb;
-    struct Fast { int band, row, b; };
+    struct Fast { int band, row, b, j0; };
     std::vector<Fast> fast;
     std::vector<int> gen;
     for (int b = 0; b < nb; ++b) {
@@ -405,25 +405,56 @@ inline void build_allpairs(HostPlan& hp) {
         const int i0 = row_of(k0), i1 = row_of(k1);
         if (i0 == i1 && k0 + kApWindow <= P) {
             const int j0 = i0 + minsep + (int)(k0 - ap.row_off[i0]);
-            fast.push_back({j0 / kApWindow, i0, b});
+            fast.push_back({j0 / kApWindow, i0, b, j0});
         } else {
             gen.push_back(b);
         }
     }
-    // Windows -> warps (two each) -> tiles (7 warps).  A warp takes the windows of two neighbouring rows in one 128-column
-    // band; a tile is 7 warps from consecutive rows of that band, so that its atoms are 14 rows' i and ~270 j.
-    // Fast tiles never straddle two bands; what is left over joins the general windows.
+    // Windows -> warps (two each) -> tiles (7 warps).
+    //  * SHARED warps (optional, see below): the same 128 columns of rows i and i + 256.  The first pairs of two rows 256 apart are a multiple
+    //    of 128 pairs apart (256 L - 255 * 128), so their window grids coincide and atom j is loaded once for both rows.
+    //    A tile is 7 such warps from consecutive rows of one band: atoms = 7 + 7 rows' i and ~270 j (up to three ranges).
+    //  * FAST warps: what has no partner 256 rows away (the windows next to the diagonal, the last rows) pairs up with the
+    //    window of a neighbouring row in the same band; tiles as above, 14 rows' i.
+    //  * what is left over joins the general windows.  Fast tiles never straddle two bands.
     struct Warp { int b0, b1; bool fast; };
     struct FastWarp { int band, row, b0, b1; };
-    std::vector<FastWarp> fw;
+    std::vector<FastWarp> shared_w, fw;
     {
+        // OFF by default: measured 7 % SLOWER on config 4 (contact map 1.131 against 1.216e12 evals/s, everything emitted
+        // 5.63 against 6.11e11).  The kernel issues at ~68 % of its slots whatever the mix -- 40 % fewer LDS in two thirds of
+        // the fast windows did not shorten it, the third launch and the extra half-filled tiles at the band ends cost more.
+        // CAVIAR_AP_SHARE=1 builds the geometry (tests keep it correct).
+        bool share = false;
+        if (const char* e = std::getenv("CAVIAR_AP_SHARE")) share = atoi(e) != 0;
         // (adjacent windows of one row -- 1 KB pieces of the matrix -- were tried and lost 4 % to the wider column bands:
         // CAVIAR_AP_PAIRING=h builds that geometry)
         bool horizontal = false;
         if (const char* e = std::getenv("CAVIAR_AP_PAIRING")) horizontal = e[0] == 'h';
-        std::vector<Fast> odd;                                   // fast is in list order: row-major, b ascending
+        std::vector<uint8_t> used(fast.size(), 0);
+        if (share) {
+            // fast is in list order (row-major, columns ascending): index of the first window of every row
+            std::vector<int> row_first((size_t)ap.n_rows + 1, -1), row_cnt((size_t)ap.n_rows + 1, 0);
+            for (size_t q = 0; q < fast.size(); ++q) { if (row_first[fast[q].row] < 0) row_first[fast[q].row] = (int)q; ++row_cnt[fast[q].row]; }
+            for (size_t q = 0; q < fast.size(); ++q) {
+                if (used[q]) continue;
+                const int r2 = fast[q].row + 256;
+                if (r2 >= ap.n_rows || row_first[r2] < 0) continue;
+                for (int c = 0; c < row_cnt[r2]; ++c) {
+                    const size_t q2 = (size_t)row_first[r2] + c;
+                    if (!used[q2] && fast[q2].j0 == fast[q].j0) {
+                        shared_w.push_back({fast[q].band, fast[q].row, fast[q].b, fast[q2].b});
+                        used[q] = used[q2] = 1;
+                        break;
+                    }
+                }
+            }
+            std::sort(shared_w.begin(), shared_w.end(), [](const FastWarp& x, const FastWarp& y) { return x.band != y.band ? x.band < y.band : x.row < y.row; });
+        }
+        std::vector<Fast> odd;
         for (size_t q = 0; q < fast.size();) {
-            if (horizontal && q + 1 < fast.size() && fast[q + 1].row == fast[q].row && fast[q + 1].b == fast[q].b + 1) {
+            if (used[q]) { ++q; continue; }
+            if (horizontal && q + 1 < fast.size() && !used[q + 1] && fast[q + 1].row == fast[q].row && fast[q + 1].b == fast[q].b + 1) {
                 fw.push_back({1000 + fast[q].band / 2, fast[q].row, fast[q].b, fast[q + 1].b});
                 q += 2;
             } else {
@@ -443,22 +474,27 @@ inline void build_allpairs(HostPlan& hp) {
     }
     std::vector<std::vector<Warp>> tiles;
     {
-        size_t q = 0;
-        while (q < fw.size()) {
-            size_t e = q;
-            while (e < fw.size() && fw[e].band == fw[q].band) ++e;
-            std::vector<Warp> cur;
-            int first_row = 0;
-            for (; q < e; ++q) {
-                // (sparse bands -- the last one only holds the rows whose alignment puts a whole window at its very start --
-                // would otherwise make tiles that span hundreds of rows, i.e. hundreds of atoms i)
-                if (!cur.empty() && fw[q].row - first_row > 96) { tiles.push_back(cur); cur.clear(); }
-                if (cur.empty()) first_row = fw[q].row;
-                cur.push_back({fw[q].b0, fw[q].b1, true});
-                if ((int)cur.size() == kApWarps) { tiles.push_back(cur); cur.clear(); }
+        auto make_tiles = [&](const std::vector<FastWarp>& list) {
+            size_t q = 0;
+            while (q < list.size()) {
+                size_t e = q;
+                while (e < list.size() && list[e].band == list[q].band) ++e;
+                std::vector<Warp> cur;
+                int first_row = 0;
+                for (; q < e; ++q) {
+                    // (sparse bands -- the last one only holds the rows whose alignment puts a whole window at its very start
+                    // -- would otherwise make tiles that span hundreds of rows, i.e. hundreds of atoms i)
+                    if (!cur.empty() && list[q].row - first_row > 96) { tiles.push_back(cur); cur.clear(); }
+                    if (cur.empty()) first_row = list[q].row;
+                    cur.push_back({list[q].b0, list[q].b1, true});
+                    if ((int)cur.size() == kApWarps) { tiles.push_back(cur); cur.clear(); }
+                }
+                if (!cur.empty()) tiles.push_back(cur);
             }
-            if (!cur.empty()) tiles.push_back(cur);
-        }
+        };
+        make_tiles(shared_w);
+        ap.n_shared_tiles = (int)tiles.size();
+        make_tiles(fw);
         ap.n_fast_windows = 0;
         ap.n_fast_tiles = (int)tiles.size();
         for (const auto& t : tiles) ap.n_fast_windows += 2 * (int)t.size();
@@ -503,25 +539,33 @@ inline void build_allpairs(HostPlan& hp) {
         int lo = 0, hi = n - 1;
         while (!need[lo]) ++lo;
         while (!need[hi]) --hi;
-        int gap_lo = -1, gap_len = 0;                              // widest hole inside [lo, hi]
+        // the two widest holes inside [lo, hi] (at least kApMinGap atoms wide) split the atoms into up to three ranges
+        int g_lo[2] = {-1, -1}, g_len[2] = {0, 0};
         for (int a = lo; a <= hi;) {
             if (need[a]) { ++a; continue; }
             int e = a;
             while (!need[e]) ++e;
-            if (e - a > gap_len) { gap_len = e - a; gap_lo = a; }
+            const int len = e - a;
+            if (len >= kApMinGap) {
+                if (len > g_len[0]) { g_lo[1] = g_lo[0]; g_len[1] = g_len[0]; g_lo[0] = a; g_len[0] = len; }
+                else if (len > g_len[1]) { g_lo[1] = a; g_len[1] = len; }
+            }
             a = e;
         }
-        t.a0 = lo / 4 * 4;
-        t.a1 = 0; t.n1 = 0;
-        if (gap_len >= kApMinGap) {
-            const int end0 = round_up(gap_lo, 4), beg1 = (gap_lo + gap_len) / 4 * 4;
-            if (beg1 > end0) {
-                t.n0 = end0 - t.a0;
-                t.a1 = beg1; t.n1 = round_up(hi + 1, 4) - beg1;
-            }
+        if (g_len[1] > 0 && g_lo[1] < g_lo[0]) { std::swap(g_lo[0], g_lo[1]); std::swap(g_len[0], g_len[1]); }   // ascending
+        if (g_len[0] == 0 && g_len[1] > 0) { g_lo[0] = g_lo[1]; g_len[0] = g_len[1]; g_len[1] = 0; }
+        int rb[3], re[3], nr = 1;                                  // ranges [rb, re), multiples of 4
+        rb[0] = lo / 4 * 4; re[0] = round_up(hi + 1, 4);
+        for (int g = 0; g < 2; ++g) {
+            if (g_len[g] == 0) continue;
+            const int end_prev = round_up(g_lo[g], 4), beg_next = (g_lo[g] + g_len[g]) / 4 * 4;
+            if (beg_next <= end_prev) continue;
+            re[nr] = re[nr - 1]; re[nr - 1] = end_prev; rb[nr] = beg_next; ++nr;
         }
-        if (t.n1 == 0) t.n0 = round_up(hi + 1, 4) - t.a0;
-        max_atoms = std::max(max_atoms, t.n0 + t.n1);
+        t.a0 = rb[0]; t.n0 = re[0] - rb[0];
+        t.a1 = nr > 1 ? rb[1] : 0; t.n1 = nr > 1 ? re[1] - rb[1] : 0;
+        t.a2 = nr > 2 ? rb[2] : 0; t.n2 = nr > 2 ? re[2] - rb[2] : 0;
+        max_atoms = std::max(max_atoms, t.n0 + t.n1 + t.n2);
     }
 
     // ring geometry: 8 frames per stage, 3 stages, 2 CTAs per SM
@@ -530,7 +574,7 @@ inline void build_allpairs(HostPlan& hp) {
     int fb = 8, ns = 3;
     if (const char* e = std::getenv("CAVIAR_AP_FB")) fb = std::max(1, std::min(32, atoi(e)));
     if (const char* e = std::getenv("CAVIAR_AP_STAGES")) ns = std::max(2, std::min(kMaxStages, atoi(e)));
-    while (fb > 1 && ns * fb * frame_b + bar_bytes > 110 * 1024) fb /= 2;
+    while (fb > 1 && ns * fb * frame_b + bar_bytes > 96 * 1024) fb /= 2;       // (8 or 4 frames per stage: no measurable difference)
     if (ns * fb * frame_b + bar_bytes > 110 * 1024) return;
     ap.frames_per_stage = fb; ap.n_stages = ns; ap.stage_floats = fb * 3 * max_atoms;
     ap.smem_bytes = ns * fb * frame_b + bar_bytes;

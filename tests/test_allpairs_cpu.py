@@ -21,7 +21,7 @@ def test_every_pair_is_evaluated_once_from_its_atoms(cb, n, m):
     assert st["windows"] == (len(pairs) + 127) // 128
     assert st["fast_windows"] >= 0.6 * st["windows"]
     # 2-D tiles: a tile streams a few hundred atoms, not the frame
-    assert st["max_tile_atoms"] <= 360 and st["mean_tile_atoms"] <= 280
+    assert st["max_tile_atoms"] <= 560 and st["mean_tile_atoms"] <= 280
     assert st["frames_per_stage"] * st["stages"] * 12 * st["max_tile_atoms"] <= st["smem_bytes"] <= 110 * 1024
     with pytest.raises(cb.CaviarError):
         plan.layout()                                             # no index tables in this mode
@@ -64,3 +64,10 @@ def test_random_geometries(cb):
         else:
             assert st["n_tiles"] == 0
     assert seen >= 20
+
+
+def test_shared_column_geometry(cb, monkeypatch):
+    monkeypatch.setenv("CAVIAR_AP_SHARE", "1")
+    for n, m in ((1000, 5), (1536, 1), (2000, 5), (1200, 40)):
+        plan = cb.FeaturePlan(n, cb.all_pairs(n, m), None, describe_only_sms=148)
+        assert plan.info["mode_name"] == "allpairs" and plan.allpairs_check()["n_tiles"] > 0

@@ -249,3 +249,23 @@ def test_random_selections_separations_and_grids(cb):
             np.testing.assert_allclose(agg.sum.cpu().numpy(), want.astype(np.float64).sum(axis=0), rtol=1e-12)
         done += 1
     assert done >= 10
+
+
+def test_shared_column_geometry_stays_correct(cb, monkeypatch):
+    """CAVIAR_AP_SHARE=1: warps that hold the same 128 columns of rows i and i + 256 (their window grids coincide) and load
+    atom j once for both -- measured slower, off by default, kept correct."""
+    import torch
+    monkeypatch.setenv("CAVIAR_AP_SHARE", "1")
+    rng = np.random.default_rng(77)
+    n, T = 1000, 45
+    xh = _frames(rng, T, n)
+    pairs = cb.all_pairs(n, 5)
+    with cb.FeaturePlan(n, pairs, None, pair_cutoff=8.0) as plan:
+        out, agg = _run(cb, plan, torch.from_numpy(xh).cuda())
+        assert plan.last_launches == 3
+    want = orc.pair_distances_f32_steps(xh, pairs[:, 0], pairs[:, 1])
+    assert out.dist.cpu().numpy().tobytes() == want.tobytes()
+    flags_want = orc.contact_flags(want, 8.0)
+    fp, _ = cb.unpack_flags(out.flags.cpu().numpy(), len(pairs), 0)
+    assert np.array_equal(fp, flags_want) and np.array_equal(out.score.cpu().numpy(), flags_want.sum(axis=1))
+    assert np.array_equal(agg.occupancy.cpu().numpy(), flags_want.sum(axis=0))
