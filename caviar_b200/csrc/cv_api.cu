@@ -424,7 +424,7 @@ static cudaError_t launch_allpairs(const CvPlan* plan, const ApParams& ap, cudaS
         if (e != cudaSuccess) return e;
         granted[dev] = smem;
     }
-    kern<<<plan->hp.ap.n_ctas / 2 * occ, kConsumerThreads + kProducerThreads, smem, st>>>(ap);
+    kern<<<plan->hp.ap.n_ctas / 2 * occ, kApThreads, smem, st>>>(ap);
     return cudaGetLastError();
 }
 

@@ -87,7 +87,16 @@ struct RunParams {
 // the frame, streamed by TMA as they are.
 constexpr int kApSlots  = 4;                       // flag words per window
 constexpr int kApWindow = 32 * kApSlots;           // pairs per window
-constexpr int kApWarps  = kConsumerThreads / 32;   // windows pairs per tile: one per consumer warp
+#ifndef CV_AP_WARPS
+#define CV_AP_WARPS 7
+#endif
+// Consumer warps of an all-pairs CTA (+ 1 producer warp).  Seven like features_kernel.  (Warp w runs on SM sub-partition
+// w % 4, so 7 + 1 warps leave one scheduler per CTA with half the work; 8 + 1 warps -- -DCV_AP_WARPS=8 -- balance them but
+// measured slower: 288 threads x 108 registers fit only ONE CTA per SM at the 4-warp allocation granularity (full flavour
+// 4.3 against 6.1e11 evals/s), and the 80-register contact-map flavour, which keeps two, lost 3 %.)
+constexpr int kApWarps  = CV_AP_WARPS;             // window pairs per tile: one per consumer warp
+constexpr int kApConsumerThreads = 32 * kApWarps;
+constexpr int kApThreads = kApConsumerThreads + kProducerThreads;
 constexpr int kApMinGap = 32;                      // atoms: a hole at least this wide splits a tile's atoms into two ranges
 
 struct ApTile {

@@ -606,7 +606,7 @@ inline void fill_info(const HostPlan& hp, CvPlanInfo& info) {
         info.mode = CV_MODE_ALLPAIRS;
         info.n_tiles = (int)hp.ap.tiles.size();
         info.n_ctas = hp.ap.n_ctas;
-        info.threads_per_cta = kConsumerThreads + kProducerThreads;
+        info.threads_per_cta = kApThreads;
         info.stages = hp.ap.n_stages;
         info.frames_per_stage = hp.ap.frames_per_stage;
         info.smem_bytes = hp.ap.smem_bytes;
