@@ -201,7 +201,7 @@ extern "C" int64_t caviar_plan_allpairs_check(const CvPlanDesc* desc, int32_t n_
     if (stats) for (int q = 0; q < 8; ++q) stats[q] = 0;
     if (!ap.on) return 0;
     const int64_t P = hp.P;
-    const int n = hp.desc.n_atoms;
+    const int n = (hp.desc.n_atoms + 3) / 4 * 4;          // tiles round their atom ranges to multiples of 4 atoms
     std::vector<uint8_t> seen((size_t)P, 0);
     int64_t max_atoms = 0, sum_atoms = 0;
     for (size_t c = 0; c < ap.tiles.size(); ++c) {
@@ -484,18 +484,30 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
     rp.coords = coords_dev;
     rp.boxrec = boxrec_dev;
     rp.n_frames = n_frames;
-    if (hp.mode == CV_MODE_STAGED) {
+    // The all-pairs flavour streams ranges of the caller's frames as they are: it needs them a multiple of 16 bytes apart
+    // and -- tiles round their atom ranges to multiples of 4 atoms -- 3 * ceil4(n_atoms) floats long (frames of a selection
+    // whose size is not a multiple of 4 must be padded: caviar_features_host does that on the way to the device).
+    const long long ap_min_stride = 3ll * ((hp.desc.n_atoms + 3) / 4 * 4);
+    const bool use_ap = hp.ap.on && frame_stride_floats % 4 == 0 && (reinterpret_cast<uintptr_t>(coords_dev) & 15) == 0 &&
+                        frame_stride_floats >= ap_min_stride;
+    if (use_ap) {
+        rp.frame_stride = frame_stride_floats;
+    } else if (hp.ap.on && hp.mode == CV_MODE_STAGED) {
+        // (no generic fall-back with the same hand-over format: the generic plan of this list wants plan-order frames)
+        return fail(CV_E_INVALID, "all-pairs plan: frames must be 16-byte aligned, a multiple of 4 floats apart and at least "
+                                  "3*ceil4(n_atoms) = " + std::to_string(ap_min_stride) + " floats long (pad the frame stride)");
+    } else if (hp.mode == CV_MODE_STAGED) {
         // plan-order frames: densely packed unless the caller says otherwise (0 = dense)
         rp.frame_stride = frame_stride_floats > 0 ? frame_stride_floats : hp.staged_floats;
         if (rp.frame_stride < hp.staged_floats || rp.frame_stride % 4 != 0)
             return fail(CV_E_INVALID, "plan-order frames: stride must be >= staged_floats_per_frame and a multiple of 4 floats");
     } else {
         if (frame_stride_floats < 3ll * hp.desc.n_atoms) return fail(CV_E_INVALID, "frame stride smaller than 3*n_atoms");
-        if (hp.mode == CV_MODE_ZEROCOPY && frame_stride_floats != 3ll * hp.desc.n_atoms && !(hp.ap.on && frame_stride_floats % 4 == 0))
+        if (hp.mode == CV_MODE_ZEROCOPY && frame_stride_floats != 3ll * hp.desc.n_atoms)
             return fail(CV_E_INVALID, "zero-copy mode needs densely packed frames (stride == 3*n_atoms)");
         rp.frame_stride = frame_stride_floats;
     }
-    if (hp.mode != CV_MODE_DIRECT && (reinterpret_cast<uintptr_t>(coords_dev) & 15) != 0)
+    if (!use_ap && hp.mode != CV_MODE_DIRECT && (reinterpret_cast<uintptr_t>(coords_dev) & 15) != 0)
         return fail(CV_E_INVALID, "coordinates must be 16-byte aligned for TMA");
     // every flavour reads the record's head with 128-bit loads (and TMA copies it whole in the ring flavours)
     if (boxrec_dev && (reinterpret_cast<uintptr_t>(boxrec_dev) & 15) != 0) return fail(CV_E_INVALID, "box records must be 16-byte aligned");
@@ -507,9 +519,6 @@ extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t f
     if (out) { rp.dist = out->dist; rp.angle = out->angle; rp.flags = out->flags; rp.score = out->score; }
     rp.P = hp.P; rp.A = hp.A; rp.W = hp.W; rp.Wp = hp.Wp;
     const long long F = hp.P + hp.A;
-    // the all-pairs flavour streams the caller's frames range by range: any stride that keeps the frames 16-byte aligned
-    const bool use_ap = hp.ap.on && frame_stride_floats % 4 == 0 && (reinterpret_cast<uintptr_t>(coords_dev) & 15) == 0 &&
-                        frame_stride_floats >= 3ll * hp.desc.n_atoms;
     Chunking ck;
     if (use_ap) {
         // The all-pairs flavour adds its aggregates in place, in chunk order (ApParams::seq): no partial rows, so chunks can
@@ -707,7 +716,9 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
     const HostPlan& hp = plan->hp;
     if (input_order != CV_ORDER_CALLER && input_order != CV_ORDER_PLAN) return fail(CV_E_INVALID, "unknown input_order");
     // frames already sliced in plan order (caviar_plan_atom_order): nothing to permute on the device
-    const bool plan_order = input_order == CV_ORDER_PLAN && hp.mode == CV_MODE_STAGED;
+    const bool ap = hp.ap.on;                      // all-pairs flavour: the caller's frames, padded to 16-byte multiples if need be
+    const bool plan_order = input_order == CV_ORDER_PLAN && hp.mode == CV_MODE_STAGED && !ap;
+    const bool staged = hp.mode == CV_MODE_STAGED && !ap;
     const int64_t min_stride = plan_order ? hp.staged_floats : 3ll * hp.desc.n_atoms;
     const int64_t P = hp.P, A = hp.A, W = hp.W, F = P + A;
     const int box_kind = hp.desc.box_kind;
@@ -737,6 +748,12 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
     const bool out_pinned = is_pinned(out->dist) && is_pinned(out->angle) && is_pinned(out->flags) && is_pinned(out->score) &&
                             is_pinned(out->score_q32);
 
+    // device-side frame stride: the caller's, unless the all-pairs flavour needs padding (selection size not a multiple of
+    // 4, or an odd stride): then the upload is a pitched copy into frames of 3 * ceil4(n_atoms) floats
+    const int64_t ap_stride = 3ll * ((hp.desc.n_atoms + 3) / 4 * 4);
+    const bool repitch = ap && (frame_stride_floats % 4 != 0 || frame_stride_floats < ap_stride);
+    const int64_t dev_stride = repitch ? ap_stride : frame_stride_floats;
+
     Trace tr;
     HostCtx& hc = plan->host;
     std::lock_guard<std::mutex> lock(hc.mu);           // one host call per plan at a time
@@ -747,8 +764,8 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
     CV_CUDA(s_up.create()); CV_CUDA(s_run.create()); CV_CUDA(s_down.create());
     CV_CUDA(ws.alloc((size_t)kQueueBytes + (size_t)hp.max_chunks * F * 24));
     for (Set& s : set) {
-        CV_CUDA(s.xyz.alloc((size_t)TB * frame_stride_floats * 4));
-        CV_CUDA(s.staged.alloc(hp.mode == CV_MODE_STAGED && !plan_order ? (size_t)TB * hp.staged_floats * 4 : 0));
+        CV_CUDA(s.xyz.alloc((size_t)TB * dev_stride * 4));
+        CV_CUDA(s.staged.alloc(staged && !plan_order ? (size_t)TB * hp.staged_floats * 4 : 0));
         CV_CUDA(s.dist.alloc(out->dist ? (size_t)TB * P * 4 : 0));
         CV_CUDA(s.angle.alloc(out->angle ? (size_t)TB * A * 4 : 0));
         CV_CUDA(s.flags.alloc(need_flags ? (size_t)TB * W * 4 : 0));
@@ -827,12 +844,16 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
             parallel_memcpy(s.h_in.p, src, (size_t)n * frame_stride_floats * 4);
             src = s.h_in.as<float>();
         }
-        CV_CUDA(cudaMemcpyAsync(s.xyz.p, src, (size_t)n * frame_stride_floats * 4, cudaMemcpyHostToDevice, s_up.s));
+        if (repitch)
+            CV_CUDA(cudaMemcpy2DAsync(s.xyz.p, (size_t)dev_stride * 4, src, (size_t)frame_stride_floats * 4, (size_t)hp.desc.n_atoms * 12, (size_t)n,
+                                      cudaMemcpyHostToDevice, s_up.s));
+        else
+            CV_CUDA(cudaMemcpyAsync(s.xyz.p, src, (size_t)n * frame_stride_floats * 4, cudaMemcpyHostToDevice, s_up.s));
         CV_CUDA(cudaEventRecord(s.uploaded.e, s_up.s));
         // compute
         CV_CUDA(cudaStreamWaitEvent(s_run.s, s.uploaded.e, 0));
         const float* coords = s.xyz.as<float>();
-        if (hp.mode == CV_MODE_STAGED && !plan_order) {
+        if (staged && !plan_order) {
             rc = caviar_stage_frames(plan, s.xyz.as<float>(), frame_stride_floats, n, s.staged.as<float>(), s_run.s);
             if (rc != CV_OK) return rc;
             launches += g_launches;
@@ -841,7 +862,7 @@ extern "C" int caviar_features_host(const CvPlan* plan, const float* xyz_host, i
         CvFrameOutputs fo{out->dist ? s.dist.as<float>() : nullptr, out->angle ? s.angle.as<float>() : nullptr,
                           need_flags ? s.flags.as<uint32_t>() : nullptr, out->score ? s.score.as<int32_t>() : nullptr};
         CvAggregates ag{occ.as<uint64_t>(), dev_moments ? sum.as<double>() : nullptr, dev_moments ? sq.as<double>() : nullptr};
-        const int64_t run_stride = (hp.mode == CV_MODE_STAGED && !plan_order) ? hp.staged_floats : frame_stride_floats;
+        const int64_t run_stride = (staged && !plan_order) ? hp.staged_floats : dev_stride;
         rc = caviar_run(plan, coords, run_stride, box_floats ? rec_all.as<float>() + t0 * kRecFloats : nullptr, n, &fo, want_agg ? &ag : nullptr, ws.p, s_run.s);
         if (rc != CV_OK) return rc;
         launches += g_launches;

@@ -366,14 +366,17 @@ inline bool is_all_pairs(const HostPlan& hp, int& minsep) {
 }
 
 // Cuts an all-pairs list into windows and 2-D tiles (cv_common.h).  Leaves hp.ap.on false when the list is not an
-// all-pairs list, when the frames cannot be streamed by TMA as they are (n_atoms % 4), or when too few windows lie
+// all-pairs list, or when too few windows lie
 // inside a single row for the geometry to pay (short rows: small selections stay on the generic kernel).
 inline void build_allpairs(HostPlan& hp) {
     ApHost& ap = hp.ap;
     ap = ApHost();
     const CvPlanDesc& d = hp.desc;
     if (d.box_kind != CV_BOX_NONE || hp.A != 0 || (d.flags & (CV_PLAN_FORCE_DIRECT | CV_PLAN_FORCE_STAGED))) return;
-    if (d.n_atoms % 4 != 0 || hp.P >= (1ll << 30) || hp.mode == CV_MODE_STAGED) return;   // (4 P bytes per row in 32 bits; staged plans take plan-order frames)
+    if (hp.P >= (1ll << 30)) return;              // (4 P bytes per row must fit 32 bits)
+    // (a generic plan of the same list that is STAGED -- it would be, for some selection sizes that are not multiples of 4 --
+    // wants plan-order frames; the all-pairs flavour takes the caller's frames, and caviar_run / caviar_features_host give
+    // it precedence: see there)
     if (const char* e = std::getenv("CAVIAR_NO_ALLPAIRS")) if (atoi(e) != 0) return;
     int minsep = 0;
     if (!is_all_pairs(hp, minsep)) return;

@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (BOX_NONE, BOX_ORTHO, BOX_TRICLINIC, CvAggregates, CvFrameOutputs, CvHostOutputs, CvPlanDesc,
-                   CvPlanInfo, MODE_DIRECT, MODE_STAGED, MODE_ZEROCOPY, ORDER_CALLER, ORDER_PLAN, PLAN_FORCE_DIRECT,
+                   CvPlanInfo, MODE_ALLPAIRS, MODE_DIRECT, MODE_STAGED, MODE_ZEROCOPY, ORDER_CALLER, ORDER_PLAN, PLAN_FORCE_DIRECT,
                    PLAN_FORCE_STAGED, check)
 
 _BOX_KINDS = {None: BOX_NONE, "none": BOX_NONE, "ortho": BOX_ORTHO, "orthorhombic": BOX_ORTHO,
@@ -232,6 +232,18 @@ class FeaturePlan:
         ``xyz[:, plan.atom_order, :]`` on the device (bit-for-bit copies).  Identity for non-staged plans.
         ``boxrec`` is accepted for source compatibility and ignored: staging is pure data movement."""
         import torch
+        if self.mode == MODE_ALLPAIRS:
+            # the all-pairs kernel streams ranges of the caller's frames: frames a multiple of 16 bytes apart and
+            # 3 * ceil4(n_atoms) floats long.  Anything else (a selection size that is not a multiple of 4) is copied
+            # once into padded frames; the view handed back has the caller's shape.
+            need = 3 * ((self.n_atoms + 3) // 4 * 4)
+            if xyz.dim() == 3 and xyz.shape[0] > 1 and xyz.stride(0) % 4 == 0 and xyz.stride(0) >= need and xyz.data_ptr() % 16 == 0:
+                return xyz
+            if xyz.dim() == 3 and xyz.shape[0] <= 1 and need == 3 * self.n_atoms and xyz.data_ptr() % 16 == 0:
+                return xyz
+            padded = torch.zeros((xyz.shape[0], need // 3, 3), dtype=torch.float32, device=xyz.device)
+            padded[:, :self.n_atoms].copy_(xyz)
+            return padded[:, :self.n_atoms]
         if self.mode != MODE_STAGED:
             return xyz
         if xyz.dtype != torch.float32 or not xyz.is_cuda:
@@ -306,7 +318,7 @@ class FeaturePlan:
             if coords.dim() != 3 or coords.shape[1] != self.n_atoms or coords.shape[2] != 3 \
                     or coords.stride(2) != 1 or coords.stride(1) != 3:
                 raise ValueError(f"frames must be (T, {self.n_atoms}, 3) with contiguous atoms")
-            stride = coords.stride(0) if coords.shape[0] > 1 else 3 * self.n_atoms
+            stride = coords.stride(0) if (coords.shape[0] > 1 or coords.stride(0) >= 3 * self.n_atoms) else 3 * self.n_atoms
         if out is None:
             out = self.alloc_outputs(T, device=coords.device)
         fo = CvFrameOutputs(*(None if t is None else t.data_ptr() for t in (out.dist, out.angle, out.flags, out.score)))

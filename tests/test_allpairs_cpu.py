@@ -11,7 +11,8 @@ def cb():
     return caviar_b200
 
 
-@pytest.mark.parametrize("n,m", [(1000, 5), (1000, 1), (1024, 3), (704, 5), (900, 7), (1200, 40), (2000, 5), (1536, 1)])
+@pytest.mark.parametrize("n,m", [(1000, 5), (1000, 1), (1024, 3), (704, 5), (900, 7), (1200, 40), (2000, 5), (1536, 1),
+                                 (1001, 5), (1003, 2), (2222, 9)])      # any selection size: frames are padded to 4-atom multiples
 def test_every_pair_is_evaluated_once_from_its_atoms(cb, n, m):
     pairs = cb.all_pairs(n, m)
     plan = cb.FeaturePlan(n, pairs, None, describe_only_sms=148)
@@ -35,8 +36,7 @@ def test_lists_that_are_not_the_reference_list_stay_on_the_generic_kernel(cb):
     for pairs in (full[:-1], full[1:], swapped, flipped, np.concatenate([full, full[:1]])):
         plan = cb.FeaturePlan(n, pairs, None, describe_only_sms=148)
         assert plan.info["mode_name"] != "allpairs" and plan.allpairs_check()["n_tiles"] == 0
-    # frames that TMA cannot stream range by range (n % 4), a box, triplets, forced modes, short rows
-    assert cb.FeaturePlan(1001, cb.all_pairs(1001, 5), None, describe_only_sms=148).info["mode_name"] != "allpairs"
+    # a box, triplets, forced modes, short rows
     assert cb.FeaturePlan(n, full, None, box="ortho", describe_only_sms=148).info["mode_name"] != "allpairs"
     assert cb.FeaturePlan(n, full, [(0, 1, 2)], describe_only_sms=148).info["mode_name"] != "allpairs"
     for force in ("direct", "staged"):
@@ -54,7 +54,7 @@ def test_random_geometries(cb):
     rng = np.random.default_rng(7)
     seen = 0
     for _ in range(60):
-        n = int(rng.integers(150, 700)) * 4
+        n = int(rng.integers(600, 2800))
         m = int(rng.integers(1, 200))
         plan = cb.FeaturePlan(n, cb.all_pairs(n, m), None, describe_only_sms=int(rng.choice([148, 132, 8])))
         st = plan.allpairs_check()

@@ -269,3 +269,41 @@ def test_shared_column_geometry_stays_correct(cb, monkeypatch):
     fp, _ = cb.unpack_flags(out.flags.cpu().numpy(), len(pairs), 0)
     assert np.array_equal(fp, flags_want) and np.array_equal(out.score.cpu().numpy(), flags_want.sum(axis=1))
     assert np.array_equal(agg.occupancy.cpu().numpy(), flags_want.sum(axis=0))
+
+
+@pytest.mark.parametrize("n", [1001, 1003, 1402])
+def test_selection_sizes_that_are_not_multiples_of_four(cb, n):
+    """Tiles round their atom ranges to 4-atom multiples (16-byte TMA granularity): the host entry point pads the frames on
+    the way to the device, device-resident callers pad with stage(); dense frames are refused with a message when the
+    generic plan of the list has a different hand-over format, and run on the generic kernel otherwise."""
+    import torch
+    rng = np.random.default_rng(n)
+    T = 23
+    xh = _frames(rng, T, n)
+    pairs = cb.all_pairs(n, 5)
+    want = orc.pair_distances_f32_steps(xh, pairs[:, 0], pairs[:, 1])
+    flags_want = orc.contact_flags(want, 8.0)
+    with cb.FeaturePlan(n, pairs, None, pair_cutoff=8.0) as plan:
+        assert plan.info["mode_name"] == "allpairs"
+        res = plan.features_host(xh, want=("dist", "score", "agg"), frames_per_block=10)
+        assert plan.last_launches >= 3 * 2                       # three blocks, two all-pairs launches each
+        assert res["dist"].tobytes() == want.tobytes()
+        assert np.array_equal(res["score"], flags_want.sum(axis=1)) and np.array_equal(res["occupancy"], flags_want.sum(axis=0))
+        x = torch.from_numpy(xh).cuda()
+        out, agg = _run(cb, plan, plan.stage(x))
+        assert plan.last_launches == 2
+        assert out.dist.cpu().numpy().tobytes() == want.tobytes()
+        assert np.array_equal(agg.occupancy.cpu().numpy(), flags_want.sum(axis=0))
+        one = plan.alloc_outputs(1, want=("dist",))
+        plan.run(plan.stage(x[3:4]), None, out=one)
+        torch.cuda.synchronize()
+        assert one.dist.cpu().numpy().tobytes() == want[3:4].tobytes()
+        try:                                                     # dense frames: generic kernel, or a clear refusal
+            out2 = plan.alloc_outputs(T, want=("dist",))
+            plan.run(x, None, out=out2)
+            torch.cuda.synchronize()
+            assert out2.dist.cpu().numpy().tobytes() == want.tobytes()
+        except cb.CaviarError as e:
+            assert "pad the frame stride" in str(e)
+    got = cb.compute_distances_parallel(xh[:5], [tuple(p) for p in pairs.tolist()])
+    assert got.tobytes() == want[:5].tobytes()
