@@ -76,7 +76,8 @@ extern "C" {
 #define CV_MODE_STAGED    2    /* frames in plan order (per-tile blocks of raw float32 xyz), TMA-streamed */
 #define CV_MODE_ALLPAIRS  3    /* the reference's own list -- all (i, j >= i + minsep), i-major (CAVIAR-1.0.py:331) -- without
                                   a box: 2-D tiles of the pair matrix, each streaming only its rows' and columns' atoms
-                                  of the caller's frames (n_atoms % 4 == 0, stride a multiple of 4 floats) */
+                                  of the caller's frames: 16-byte aligned, a multiple of 4 floats apart and at least
+                                  3 * ceil4(n_atoms) floats long -- caviar_features_host pads on upload when they are not */
 
 /* atom order of the frames handed to caviar_features_host */
 #define CV_ORDER_CALLER   0    /* (T, n_atoms, 3) as the pair / triplet lists index it */
@@ -188,7 +189,10 @@ int caviar_stage_frames(const CvPlan* plan, const float* xyz_dev, int64_t frame_
 /* The fused hot path over n_frames frames resident on the device.
  *   coords: CV_MODE_STAGED -> frames in plan order, raw float32 xyz (frame_stride_floats apart, 0 = densely packed,
  *           otherwise >= staged_floats_per_frame and a multiple of 4); otherwise the caller's frames themselves
- *           (frame_stride_floats apart; CV_MODE_ZEROCOPY needs stride == 3*n_atoms).
+ *           (frame_stride_floats apart; CV_MODE_ZEROCOPY needs stride == 3*n_atoms; CV_MODE_ALLPAIRS takes frames that
+ *           are 16-byte aligned, a multiple of 4 floats apart and >= 3*ceil4(n_atoms) floats long, adds the aggregates in
+ *           place -- no finalize launch -- and otherwise falls back to the generic kernel of the same list where that
+ *           kernel takes the same frames, or fails with CV_E_INVALID asking for the padding).
  *           With a box, atoms may sit anywhere (unwrapped trajectories included): displacements are minimum-imaged.
  *   boxrec: prepared records, NULL iff box_kind == CV_BOX_NONE.
  * Launches on `stream` (a cudaStream_t) and returns without synchronising. */
