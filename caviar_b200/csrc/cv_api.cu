@@ -452,6 +452,19 @@ static bool make_chunks(int64_t n_frames, int64_t fb, int max_chunks, int64_t n_
     c.tail_frames = (int32_t)tf;
     c.n_big_chunks = (int32_t)n_big;
     c.n_chunks = (int32_t)(n_big + n_small);
+    // Very short runs (fewer items than CTAs: config 1 has 42 on 296): the pass is ONE CTA's chain of stage round
+    // trips, so the frames are cut finer -- uniform chunks, down to kTinyChunkFrames -- until every CTA has an item.
+    int64_t tiny_floor = kTinyChunkFrames;
+    if (const char* e = std::getenv("CAVIAR_TINY_CHUNK")) tiny_floor = std::max(1, atoi(e));       // A/B: tools/gpu_short_runs.py
+    if ((int64_t)c.n_chunks * n_tiles < n_ctas) {
+        const int64_t want = (n_ctas + n_tiles - 1) / n_tiles;                   // chunks that make one item per CTA
+        const int64_t tiny = std::max<int64_t>(tiny_floor, (n_frames + want - 1) / want);
+        const int64_t n_tiny = (n_frames + tiny - 1) / tiny;
+        if (tiny < cf && n_tiny <= max_chunks) {
+            c.chunk_frames = (int32_t)tiny; c.tail_frames = (int32_t)tiny;
+            c.n_big_chunks = (int32_t)n_tiny; c.n_chunks = (int32_t)n_tiny;
+        }
+    }
     return true;
 }
 

@@ -142,6 +142,7 @@ constexpr int kMinChunkFrames = 32;     // ... but never fewer frames per item t
 constexpr int kMinTailFrames = 8;       // ... except the quarter-size items of the tail (per-item flush = 24 B per feature)
 constexpr int kFinalizeSlicesFew = 8, kFinalizeSlicesMany = 32;   // chunk slices summed in parallel, combined in a fixed order
 constexpr int kFinalizeManyRows = 128;   // from this many chunk rows on, the 32-slice shape
+constexpr int kTinyChunkFrames = 4;     // ... and runs with fewer items than CTAs are cut down to this (latency chain of one CTA, config 1)
 constexpr int kItemsPerCta = 32;        // work items per CTA the chunking aims for (tail imbalance <= ~1/16)
 
 }  // namespace cv
