@@ -344,6 +344,37 @@ class FeaturePlan:
         self.last_launches = int(_lib.lib.caviar_last_launch_count())
         return out
 
+    def capture(self, coords, boxrec=None, out: Optional[FrameOutputs] = None, aggregates: Optional[Aggregates] = None,
+                workspace=None, n_frames: Optional[int] = None):
+        """Record one pass of ``run`` over these buffers -- its two memsets, the fused kernel and the finalize kernel --
+        as a CUDA graph.  ``graph.replay()`` then repeats the pass for one launch's worth of host time: short passes
+        (BASELINE config 1: ~20 us of device time) are otherwise bound by the host enqueueing four stream operations.
+        Nothing is executed on the caller's buffers except ``out`` (written once by the warm-up, as a replay would);
+        ``aggregates`` are accumulated into by every replay, not by this call.  Returns ``(graph, out)``."""
+        import torch
+        T = coords.shape[0] if n_frames is None else int(n_frames)
+        if out is None:
+            out = self.alloc_outputs(T, device=coords.device)
+        if workspace is None:
+            if getattr(self, "_ws", None) is None or self._ws.device != coords.device:
+                self._ws = self.new_workspace(coords.device)
+            workspace = self._ws
+        scratch = None
+        if aggregates is not None:      # same kernel flavour as the recorded pass, on throw-away totals
+            scratch = Aggregates(torch.zeros_like(aggregates.occupancy),
+                                 None if aggregates.sum is None else torch.zeros_like(aggregates.sum),
+                                 None if aggregates.sumsq is None else torch.zeros_like(aggregates.sumsq))
+        side = torch.cuda.Stream(device=coords.device)
+        side.wait_stream(torch.cuda.current_stream(coords.device))
+        with torch.cuda.stream(side):   # one-time set-up (shared-memory opt-in of the flavour) must not fall into the capture
+            self.run(coords, boxrec, out=out, aggregates=scratch, workspace=workspace, n_frames=T)
+        torch.cuda.current_stream(coords.device).wait_stream(side)
+        torch.cuda.synchronize(coords.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.run(coords, boxrec, out=out, aggregates=aggregates, workspace=workspace, n_frames=T)
+        return graph, out
+
     def residue_components(self, sum_a, n_frames: int, cut: float, sum_b=None, n_frames_b: int = 0):
         """Component label of every residue (= atom of this plan) on the device: ``build_residue_components``
         (CAVIAR-1.0.py:183-199) over the per-pair time means ``sum / T`` -- or, with ``sum_b``, the pooled mean of two

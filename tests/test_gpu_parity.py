@@ -419,6 +419,34 @@ def test_aggregates_are_bit_reproducible_run_to_run(cb):
             assert torch.equal(a, b)
 
 
+def test_graph_replay_equals_eager_runs_on_a_short_pass(cb):
+    """``FeaturePlan.capture``: a short pass (config-1 shape: fewer work items than CTAs, i.e. the tiny-chunk rule of
+    make_chunks) recorded as a CUDA graph; two replays must leave exactly what two eager runs leave -- per-frame outputs
+    and accumulated aggregates, bit for bit -- and the capture itself must not touch the caller's totals."""
+    import torch
+    from caviar_b200 import synthetic as syn
+    top = syn.make_topology(1)
+    T = 1000
+    pairs, triplets = syn.compact_indices(top)
+    x = syn.device_frames(top, T, only_referenced=True)
+    with cb.FeaturePlan(x.shape[1], pairs, triplets) as plan:
+        coords = plan.stage(x)
+        agg_e = plan.new_aggregates()
+        out_e = plan.run(coords, aggregates=agg_e)
+        plan.run(coords, out=out_e, aggregates=agg_e)
+        torch.cuda.synchronize()
+        agg_g = plan.new_aggregates()
+        graph, out_g = plan.capture(coords, aggregates=agg_g)
+        torch.cuda.synchronize()
+        assert int(agg_g.occupancy.sum()) == 0 and float(agg_g.sum.abs().sum()) == 0.0
+        graph.replay(); graph.replay()
+        torch.cuda.synchronize()
+        for a, b in ((out_e.dist, out_g.dist), (out_e.angle, out_g.angle), (out_e.flags, out_g.flags), (out_e.score, out_g.score),
+                     (agg_e.occupancy, agg_g.occupancy), (agg_e.sum, agg_g.sum), (agg_e.sumsq, agg_g.sumsq)):
+            assert torch.equal(a, b)
+        assert int(agg_e.occupancy.sum()) > 0
+
+
 def test_integration_md_ctypes_stub(cb, gold):
     """The raw-ctypes binding INTEGRATION.md shows a maintainer (no caviar_b200 import on the call path)."""
     import ctypes
