@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Short runs (BASELINE config 1 and 2 and shorter pieces of them): time per pass against the floor of the tiny-run
-chunking (GPU box only).  CAVIAR_TINY_CHUNK is read by make_chunks() (cv_api.cu) on every run; 100000 = rule off."""
+chunking (GPU box only).  CAVIAR_TINY_CHUNK is read by make_chunks() (cv_api.cu) on every run; 100000 = rule off.
+Timed as CUDA-graph replays of one pass (FeaturePlan.capture)."""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,14 +9,12 @@ import caviar_b200 as cb
 from caviar_b200 import synthetic as syn
 
 peak = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"] if os.path.exists("MEASURED_PEAKS.json") else 6557.4
-KNOBS = [("tiny_off", {"CAVIAR_TINY_CHUNK": "100000"}),
+KNOBS = [("default", {}),
          ("tiny2", {"CAVIAR_TINY_CHUNK": "2"}),
-         ("tiny4 (default)", {}),
-         ("tiny6", {"CAVIAR_TINY_CHUNK": "6"}),
          ("tiny8", {"CAVIAR_TINY_CHUNK": "8"}),
-         ("tiny12", {"CAVIAR_TINY_CHUNK": "12"}),
          ("tiny16", {"CAVIAR_TINY_CHUNK": "16"}),
-         ("tiny_off_again", {"CAVIAR_TINY_CHUNK": "100000"})]
+         ("tiny_off", {"CAVIAR_TINY_CHUNK": "100000"}),
+         ("default_again", {})]
 for cfg_id, T in ((1, 1000), (1, 250), (1, 4000), (2, 1000), (2, 10000)):
     top = syn.make_topology(cfg_id)
     pairs, triplets = syn.compact_indices(top)
@@ -42,13 +41,14 @@ for cfg_id, T in ((1, 1000), (1, 250), (1, 4000), (2, 1000), (2, 10000)):
             chk = (out.dist.view(torch.int32).sum().item(), int(agg.occupancy.sum().item()), float(agg.sum.sum().item()))
             if ref is None:
                 ref = chk
+            graph, _ = plan.capture(coords, rec, out=out, aggregates=agg, workspace=ws)     # the knobs are read while recording
             for _ in range(5):
-                plan.run(coords, rec, out=out, aggregates=agg, workspace=ws)
+                graph.replay()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = 50
+            reps = 200
             torch.cuda.synchronize(); e0.record()
             for _ in range(reps):
-                plan.run(coords, rec, out=out, aggregates=agg, workspace=ws)
+                graph.replay()
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / reps
             alg = info["algorithmic_bytes_per_frame"] * T
