@@ -69,6 +69,7 @@ class CvHostOutputs(C.Structure):
 # every symbol include/caviar_b200.h declares: (restype, argtypes)
 SYMBOLS = {
     "caviar_plan_describe": (C.c_int, [C.POINTER(CvPlanDesc), C.c_int32, C.POINTER(CvPlanInfo)]),
+    "caviar_plan_chunks": (C.c_int, [C.POINTER(CvPlanDesc), C.c_int32, C.c_int64, C.c_void_p]),
     "caviar_plan_layout": (C.c_int, [C.POINTER(CvPlanDesc), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "caviar_plan_allpairs_check": (C.c_int64, [C.POINTER(CvPlanDesc), C.c_int32, C.c_void_p]),
     "caviar_plan_create": (C.c_int, [C.POINTER(CvPlanDesc), C.POINTER(C.c_void_p)]),

@@ -456,7 +456,7 @@ static bool make_chunks(int64_t n_frames, int64_t fb, int max_chunks, int64_t n_
     // trips, so the frames are cut finer -- uniform chunks, down to kTinyChunkFrames -- until every CTA has an item.
     int64_t tiny_floor = kTinyChunkFrames;
     if (const char* e = std::getenv("CAVIAR_TINY_CHUNK")) tiny_floor = std::max(1, atoi(e));       // A/B: tools/gpu_short_runs.py
-    if ((int64_t)c.n_chunks * n_tiles < n_ctas) {
+    if (uniform_items < n_ctas) {                       // (counted before the quarter-size tail, which only adds small items)
         const int64_t want = (n_ctas + n_tiles - 1) / n_tiles;                   // chunks that make one item per CTA
         const int64_t tiny = std::max<int64_t>(tiny_floor, (n_frames + want - 1) / want);
         const int64_t n_tiny = (n_frames + tiny - 1) / tiny;
@@ -466,6 +466,19 @@ static bool make_chunks(int64_t n_frames, int64_t fb, int max_chunks, int64_t n_
         }
     }
     return true;
+}
+
+extern "C" int caviar_plan_chunks(const CvPlanDesc* desc, int32_t n_sms, int64_t n_frames, int32_t* out) {
+    if (!desc || !out) return fail(CV_E_INVALID, "null argument");
+    if (n_frames <= 0) return fail(CV_E_INVALID, "n_frames must be positive");
+    HostPlan hp;
+    std::string why = build_plan(*desc, n_sms, hp);
+    if (!why.empty()) return fail(CV_E_INVALID, why);
+    Chunking ck;
+    if (!make_chunks(n_frames, hp.frames_per_stage, hp.max_chunks, (int64_t)hp.tiles.size(), hp.n_ctas, ck))
+        return fail(CV_E_INVALID, "too many frames for one run: split the call");
+    out[0] = ck.chunk_frames; out[1] = ck.tail_frames; out[2] = ck.n_big_chunks; out[3] = ck.n_chunks;
+    return CV_OK;
 }
 
 extern "C" int caviar_run(const CvPlan* plan, const float* coords_dev, int64_t frame_stride_floats,

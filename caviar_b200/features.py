@@ -160,6 +160,12 @@ class FeaturePlan:
         keys = ("windows", "fast_windows", "max_tile_atoms", "frames_per_stage", "stages", "smem_bytes", "mean_tile_atoms", "n_ctas")
         return {"n_tiles": int(got), **{k: int(v) for k, v in zip(keys, stats)}}
 
+    def chunks(self, n_frames: int) -> dict:
+        """How ``run`` would cut ``n_frames`` frames into the frame chunks of its work queue (host-side, no CUDA)."""
+        out = np.zeros(4, dtype=np.int32)
+        check(_lib.lib.caviar_plan_chunks(C.byref(self._desc), self._sms, int(n_frames), out.ctypes.data))
+        return {"chunk_frames": int(out[0]), "tail_frames": int(out[1]), "n_big_chunks": int(out[2]), "n_chunks": int(out[3])}
+
     def layout(self) -> dict:
         """The planner's tables (host-side, no CUDA): ``tiles`` (n_tiles, 8) = kind, f_begin, n_feat, idx_off, grp_off,
         grp_floats, 0, 0; ``idx`` (3, n_tiles*896) float offsets inside a tile's block; ``src_off`` (S,)."""

@@ -149,6 +149,12 @@ typedef struct CvAggregates {
 /* Host-side planning only (no CUDA call): what plan_create would decide. */
 int caviar_plan_describe(const CvPlanDesc* desc, int32_t n_sms, CvPlanInfo* info);
 
+/* Host-side planning only (no CUDA call): how caviar_run would cut a run of n_frames frames into the frame chunks of its
+ * work queue (generic kernels; the all-pairs flavour chunks on its own).  out[4] = {chunk_frames, tail_frames, n_big_chunks,
+ * n_chunks}: chunks [0, n_big_chunks) hold chunk_frames frames each, the rest tail_frames each (the last one clipped at
+ * n_frames); n_chunks never exceeds CvPlanInfo.partial_slots.  For CPU-side verification that every frame is covered once. */
+int caviar_plan_chunks(const CvPlanDesc* desc, int32_t n_sms, int64_t n_frames, int32_t* out);
+
 /* Host-side planning only: the layout tables a plan would upload, for CPU-side verification of the planner.
  *   tile_desc [n_tiles][8] int32 = {kind, f_begin, n_feat, idx_off, grp_off, grp_floats, 0, 0}
  *   idx       [3][n_tiles*896] int32: float offset (3*slot) of atom role 0/1/2 inside the tile's block

@@ -250,3 +250,30 @@ def test_plain_c_host_links_against_the_abi(cb, tmp_path):
         assert res.returncode == 0 and "frame 1: 5.0000 20.0000 5.0000" in res.stdout
     else:
         assert res.returncode == 2 and "no CPU fallback" in res.stdout
+
+
+def test_run_chunks_cover_every_frame_once(cb):
+    """caviar_plan_chunks: the frame chunks of the work queue (make_chunks in cv_api.cu) tile [0, n_frames) exactly, fit the
+    partial-aggregate slots, and runs too short to give every CTA an item are cut finer (down to 4 frames)."""
+    from caviar_b200 import synthetic as syn
+    rng = np.random.default_rng(11)
+    for cfg_id in (1, 2, 3):
+        top = syn.make_topology(cfg_id)
+        pairs, trips = syn.compact_indices(top)
+        plan = cb.FeaturePlan(len(top.referenced), pairs, trips if len(trips) else None, box=top.cfg.box, describe_only_sms=148)
+        slots, n_tiles, n_ctas = plan.info["partial_slots"], plan.info["n_tiles"], plan.info["n_ctas"]
+        for T in [1, 2, 3, 5, 31, 32, 33, 250, 1000, 4000, 4096, 10000, 100000, 1234567] + [int(t) for t in rng.integers(1, 300000, 40)]:
+            ck = plan.chunks(T)
+            cf, tf, nb, nc = ck["chunk_frames"], ck["tail_frames"], ck["n_big_chunks"], ck["n_chunks"]
+            assert cf >= 1 and tf >= 1 and 0 <= nb <= nc <= slots, (cfg_id, T, ck)
+            start = lambda c: c * cf if c < nb else nb * cf + (c - nb) * tf
+            assert start(nc - 1) < T <= start(nc), (cfg_id, T, ck)          # last chunk is non-empty and reaches the end
+            if nb < nc:
+                assert nb * cf <= T                                          # the big chunks never run past the end
+            if nb == nc and cf < 32:                                         # the fine chunks of a short run:
+                assert cf >= 4 and (nc * n_tiles <= n_ctas + n_tiles or cf == 4), (cfg_id, T, ck)   # about one item per CTA
+        if cfg_id == 1:                                                      # 2 tiles on 296 CTAs: 148 chunks wanted
+            assert plan.chunks(1000)["chunk_frames"] == 7 and plan.chunks(4000)["chunk_frames"] == 28
+            assert plan.chunks(250)["chunk_frames"] == 4 and plan.chunks(100000)["chunk_frames"] >= 32
+        with pytest.raises(cb.CaviarError):
+            plan.chunks(0)

@@ -10,12 +10,10 @@ from caviar_b200 import synthetic as syn
 
 peak = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"] if os.path.exists("MEASURED_PEAKS.json") else 6557.4
 KNOBS = [("default", {}),
-         ("tiny2", {"CAVIAR_TINY_CHUNK": "2"}),
          ("tiny8", {"CAVIAR_TINY_CHUNK": "8"}),
-         ("tiny16", {"CAVIAR_TINY_CHUNK": "16"}),
          ("tiny_off", {"CAVIAR_TINY_CHUNK": "100000"}),
          ("default_again", {})]
-for cfg_id, T in ((1, 1000), (1, 250), (1, 4000), (2, 1000), (2, 10000)):
+for cfg_id, T in ((1, 1000), (1, 250), (1, 2000), (1, 4000), (1, 6000), (2, 500), (2, 1000), (2, 2000), (2, 10000)):
     top = syn.make_topology(cfg_id)
     pairs, triplets = syn.compact_indices(top)
     U = len(top.referenced)
