@@ -97,6 +97,8 @@ SYMBOLS = {
                                            C.c_void_p]),
     "caviar_compact_frames_soa_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64,
                                                C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "caviar_mdcrd_decode_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
+                                         C.c_void_p, C.c_int64, C.c_void_p]),
     "caviar_xtc_index": (C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int32)]),
     "caviar_xtc_decode_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_float,
                                          C.c_void_p, C.c_void_p]),

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libcaviar_b200.so")
-SOURCES = ["cv_api.cu", "cv_cov.cu", "cv_xtc.cu"]
+SOURCES = ["cv_api.cu", "cv_cov.cu", "cv_xtc.cu", "cv_mdcrd.cu"]
 HEADERS = ["cv_device.cuh", "cv_allpairs.cuh", "cv_plan.hpp", "cv_common.h", os.path.join("..", "..", "include", "caviar_b200.h")]
 
 NVCC_FLAGS = [

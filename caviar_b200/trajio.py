@@ -340,8 +340,14 @@ class Trajectory:
         n = len(range(lo, hi, stride))
         if out is None:
             out = np.empty((n, len(atoms), 3), dtype=np.float32)
-        if self._crd is not None:                                  # text: parse the frames, then pick the atoms
-            out[...] = self._crd.coords(lo, hi, stride)[:, atoms, :]
+        if self._crd is not None:                                  # text, fixed-width fields: only the selected atoms are parsed
+            sel = np.asarray(atoms)
+            if n and len(sel) and (sel.min() < 0 or sel.max() >= self.n_atoms):
+                raise IndexError(f"atom index out of range for {self.n_atoms} atoms")
+            if out.dtype == np.float32 and out.flags.c_contiguous and out.shape == (n, len(sel), 3):
+                self._crd.read(np.arange(lo, hi, stride), sel, out)
+            else:
+                out[...] = self._crd.coords(lo, hi, stride)[:, sel, :]
             return out
         if self._xtc is not None:                                  # decompressed frame by frame on the host threads, in Angstrom
             if n and len(atoms):
@@ -628,7 +634,32 @@ class _MdcrdFile:
     def _numbers(self, raw: np.ndarray) -> np.ndarray:
         return np.char.strip(raw.view("S8")).astype(np.float64)
 
+    def read(self, frames: np.ndarray, atoms: Optional[np.ndarray], out: np.ndarray) -> None:
+        """Frames ``frames`` (indices), atoms ``atoms`` (None: all) -> ``out`` (n, n_sel, 3) float32: the fixed-width
+        fields of the selected atoms only, parsed by the native library on the host threads (``cv_mdcrd.cu``)."""
+        from . import _lib
+        frames = np.ascontiguousarray(frames, dtype=np.int64)
+        if atoms is not None:
+            atoms = np.ascontiguousarray(atoms, dtype=np.int32)
+        if len(frames) == 0 or (atoms is not None and len(atoms) == 0):
+            return
+        try:
+            _lib.check(_lib.lib.caviar_mdcrd_decode_host(self._mm.ctypes.data, self._mm.size, self.first, self.frame_bytes, self.eol,
+                                                         self.n_atoms, frames.ctypes.data, len(frames),
+                                                         None if atoms is None else atoms.ctypes.data,
+                                                         0 if atoms is None else len(atoms), out.ctypes.data))
+        except _lib.CaviarError as e:                              # what the numpy string conversion raised
+            raise ValueError(str(e)) from None
+
     def coords(self, lo: int, hi: int, stride: int = 1) -> np.ndarray:
+        idx = np.arange(lo, hi, max(1, stride))
+        out = np.empty((len(idx), self.n_atoms, 3), dtype=np.float32)
+        self.read(idx, None, out)
+        return out
+
+    def coords_numpy(self, lo: int, hi: int, stride: int = 1) -> np.ndarray:
+        """The same through numpy's string -> float64 conversion (single-threaded, every atom): kept as the checker of
+        the native parser in the tests."""
         idx = np.arange(lo, hi, max(1, stride))
         out = np.empty((len(idx), self.n_atoms, 3), dtype=np.float32)
         for k, t in enumerate(idx):

@@ -308,6 +308,16 @@ int64_t caviar_xtc_index(const void* data, int64_t size, int64_t* offsets, int64
 int caviar_xtc_decode_host(const void* data, int64_t size, const int64_t* offsets, int64_t n_frames,
                            const int32_t* atoms, int64_t n_sel, float scale, float* xyz_out, float* box_out);
 
+/* Amber ASCII trajectories (mdcrd; the reference CLI advertises them, CAVIAR_Distances-Extractor.py:99, and leaves them
+ * to cpptraj): 3N numbers per frame in Fortran 10F8.3 -- fixed positions, so only the selected atoms are parsed, frames in
+ * parallel on the host threads (cv_mdcrd.cu).  `data` / `size`: the file image; `first`: byte of the first frame (after the
+ * title line); `frame_bytes`: distance between frames (coordinates + optional box line); `eol`: 1 = LF, 2 = CR LF;
+ * frames[0 .. n_frames): frame indices -> xyz_out [n_frames][n_sel][3] float32 (atoms == NULL: all n_atoms), in the
+ * file's unit (Angstrom).  A field that is not a number is CV_E_INVALID naming the frame. */
+int caviar_mdcrd_decode_host(const void* data, int64_t size, int64_t first, int64_t frame_bytes, int32_t eol,
+                             int32_t n_atoms, const int64_t* frames, int64_t n_frames, const int32_t* atoms,
+                             int64_t n_sel, float* xyz_out);
+
 /* Host-side CSV row formatter for the Extractor output (CAVIAR_Distances-Extractor.py:147-151,196-198: one frame
  * column, then one distance column per pair).  Formats rows x cols float32 values as
  *     "<first_index + r*index_step>,<v>,<v>,...<EOL>"    with `decimals` fixed decimals (printf "%.Nf" rounding)

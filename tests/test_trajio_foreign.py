@@ -291,3 +291,44 @@ def test_xtc_writer_reader_round_trip_with_runs_and_radix_changes(trajio, tmp_pa
         assert np.array_equal(tr.coords(0, T), want * np.float32(10.0))
         assert np.abs(want - xyz * np.float32(scale)).max() <= 0.0005 * max(1.0, scale / 64)
         tr.close()
+
+
+def test_mdcrd_native_parser_equals_numpy_conversion_on_odd_fields(trajio, tmp_path):
+    """cv_mdcrd.cu against numpy's string -> float64 conversion (the parser trajio used before), bit for bit: touching
+    negative fields, Fortran's omitted leading zero, an explicit plus sign, left-justified and integer fields, NaN; CR LF
+    lines; a selection in arbitrary order with repeats.  A field that is no number ('********') is a ValueError both ways."""
+    rng = np.random.default_rng(3)
+    n, T = 23, 5
+    fields = ["%8.3f" % v for v in rng.uniform(-999.0, 9999.0, size=T * 3 * n)]
+    odd = ["   -.123", "    .500", "  +1.500", "1.5     ", "     -12", "12345678", "     NaN", "-999.999", "9999.999", "  -0.000"]
+    for k, f in enumerate(odd):
+        fields[7 * k + 3] = f
+    for eol in ("\n", "\r\n"):
+        text = "odd fields" + eol
+        for t in range(T):
+            row = fields[t * 3 * n:(t + 1) * 3 * n]
+            for k in range(0, len(row), 10):
+                text += "".join(row[k:k + 10]) + eol
+            text += "%8.3f%8.3f%8.3f" % (50.0, 60.0, 70.0) + eol
+        p = tmp_path / ("odd%d.mdcrd" % len(eol))
+        p.write_bytes(text.encode())
+        tr = trajio.Trajectory(str(p), n_atoms=n)
+        assert tr.n_frames == T and tr.box_kind() == "ortho"
+        want = tr._crd.coords_numpy(0, T)
+        got = tr.coords(0, T)
+        assert got.tobytes() == want.tobytes()
+        assert np.isnan(got).sum() == 1
+        sel = np.array([n - 1, 0, 7, 7, 3], dtype=np.int64)
+        assert tr.coords_of(sel, 1, T, 2).tobytes() == np.ascontiguousarray(want[1:T:2][:, sel, :]).tobytes()
+        with pytest.raises(IndexError):
+            tr.coords_of(np.array([n]), 0, T)
+        tr.close()
+    bad = text.replace(fields[5], "********", 1)
+    pb = tmp_path / "bad.mdcrd"
+    pb.write_bytes(bad.encode())
+    tr = trajio.Trajectory(str(pb), n_atoms=n)
+    with pytest.raises(ValueError):
+        tr.coords(0, T)
+    with pytest.raises(ValueError):
+        tr._crd.coords_numpy(0, T)
+    tr.close()
