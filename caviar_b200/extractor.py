@@ -124,10 +124,10 @@ def select_atoms(top, labels: Sequence[PairLabel], numbering: str, offset: int) 
     return out
 
 
-def format_rows(values: np.ndarray, first_index: int, step: int, decimals: int, crlf: bool = True) -> bytes:
+def format_rows(values: np.ndarray, first_index: int, step: int, decimals: int, crlf: bool = True, copy: bool = True):
     """``index,v,v,...`` lines through the native formatter (caviar_format_csv).  Lines end in CR LF by default: the
     reference writes its rows through ``csv.writer`` (CAVIAR_Distances-Extractor.py:196-198), whose line terminator
-    that is."""
+    that is.  ``copy=False`` returns a memoryview of the formatter's buffer (what a file's ``write`` takes) instead of bytes."""
     from . import _lib
     values = np.ascontiguousarray(values, dtype=np.float32)
     rows, cols = values.shape
@@ -141,7 +141,7 @@ def format_rows(values: np.ndarray, first_index: int, step: int, decimals: int, 
             break
     if n < 0:
         _lib.check(int(n))
-    return buf[:n].tobytes()
+    return buf[:n].tobytes() if copy else memoryview(buf[:n])
 
 
 def build_parser() -> argparse.ArgumentParser:
@@ -222,7 +222,7 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
             xyz = traj.coords_of(sel, lo, hi, stride)           # native multi-threaded gather (+ byte order) from the mapped file
             cell = traj.cell(lo, hi, stride) if box_kind else None
             res = plan.features_host(xyz, cell, want=want, weights=weights, plan_order=order is not None)
-            fout.write(format_rows(res["dist"], b0 + 1, 1, args.decimals))       # cpptraj's 1-based set index
+            fout.write(format_rows(res["dist"], b0 + 1, 1, args.decimals, copy=False))       # cpptraj's 1-based set index
             if npy is not None:
                 npy[b0:b0 + len(ids)] = res["dist"]
             occ += res["occupancy"]; s1 += res["sum"]; s2 += res["sumsq"]

@@ -669,12 +669,11 @@ class _MdcrdFile:
         return out
 
     def box(self, lo: int, hi: int, stride: int = 1) -> np.ndarray:
-        idx = np.arange(lo, hi, max(1, stride))
-        out = np.empty((len(idx), 3), dtype=np.float32)
-        for k, t in enumerate(idx):
-            o = self.first + int(t) * self.frame_bytes + self.coord_bytes
-            out[k] = self._numbers(np.ascontiguousarray(np.asarray(self._mm[o:o + 24])))
-        return out
+        idx = np.arange(lo, hi, max(1, stride), dtype=np.int64)
+        if len(idx) == 0:
+            return np.empty((0, 3), dtype=np.float32)
+        pos = (self.first + idx * self.frame_bytes + self.coord_bytes)[:, None] + np.arange(24, dtype=np.int64)[None, :]
+        return self._numbers(np.ascontiguousarray(self._mm[pos.ravel()])).reshape(len(idx), 3).astype(np.float32)   # all box lines at once
 
     def close(self):
         self._mm = None
