@@ -332,3 +332,44 @@ def test_mdcrd_native_parser_equals_numpy_conversion_on_odd_fields(trajio, tmp_p
     with pytest.raises(ValueError):
         tr._crd.coords_numpy(0, T)
     tr.close()
+
+
+def test_mdcrd_native_parser_random_fields(trajio, tmp_path):
+    """20 000 random eight-character fields in several fixed-point shapes (F8.1 ... F8.5, integers, left-justified,
+    leading zero dropped): the native parser must return numpy's correctly rounded conversion, bit for bit."""
+    rng = np.random.default_rng(17)
+    n, T = 667, 10                                     # 3 * 667 = 2001 values per frame: a ragged last line
+    fields = []
+    for k in range(T * 3 * n):
+        kind = k % 7
+        if kind == 0:
+            f = "%8.3f" % rng.uniform(-999.0, 9999.0)
+        elif kind == 1:
+            f = "%8.1f" % rng.uniform(-99999.0, 999999.0)
+        elif kind == 2:
+            f = "%8.5f" % rng.uniform(-9.0, 99.0)
+        elif kind == 3:
+            f = "%8d" % rng.integers(-999999, 9999999)
+        elif kind == 4:
+            f = "%-8.3f" % rng.uniform(-99.0, 999.0)
+        elif kind == 5:
+            f = ("%8.3f" % rng.uniform(-0.999, 0.999)).replace("0.", " .", 1).replace("- .", " -.", 1)
+        else:
+            f = "%8.2f" % rng.uniform(-9999.0, 99999.0)
+        assert len(f) == 8, f
+        fields.append(f)
+    text = "random fields\n"
+    for t in range(T):
+        row = fields[t * 3 * n:(t + 1) * 3 * n]
+        for k in range(0, len(row), 10):
+            text += "".join(row[k:k + 10]) + "\n"
+    p = tmp_path / "random.mdcrd"
+    p.write_bytes(text.encode())
+    tr = trajio.Trajectory(str(p), n_atoms=n)
+    assert tr.n_frames == T and tr.box_kind() is None
+    want = np.array([float(f) for f in fields], dtype=np.float64).astype(np.float32).reshape(T, n, 3)
+    assert tr.coords(0, T).tobytes() == want.tobytes()
+    assert tr._crd.coords_numpy(0, T).tobytes() == want.tobytes()
+    sel = rng.integers(0, n, size=100)
+    assert tr.coords_of(sel, 0, T, 3).tobytes() == np.ascontiguousarray(want[0:T:3][:, sel, :]).tobytes()
+    tr.close()
