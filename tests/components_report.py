@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""f4 (CAVIAR-1.0.py:183-199): residue components of the thresholded mean-distance graph -- device kernel fed by the fused
+"""GPU box: python tests/components_report.py   (lives under tests/ because it uses the oracle as the checker)
+f4 (CAVIAR-1.0.py:183-199): residue components of the thresholded mean-distance graph -- device kernel fed by the fused
 kernel's fp64 sums, against the reference's algorithm (dict of pair means + Python DFS, oracle port) on the host (GPU box only)."""
 import sys, os, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
